@@ -1,0 +1,210 @@
+/*
+ * saa_b200.h -- C ABI of libsaa_b200.so
+ *
+ * B200 (sm_100a) implementation of the sample-average-approximation (SAA)
+ * "linearize + assemble" step of StanfordASL/RiskAverseTrajOpt.  Every entry
+ * point below replaces a Python/JAX method of the reference's per-script
+ * `Model` class; the citation after "replaces:" is the reference file:line.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no C++/torch types.  `stream` is a
+ *     cudaStream_t passed as void* (NULL = the legacy default stream).
+ *   - pointers named *_dev are device pointers owned by the CALLER (e.g. the
+ *     data_ptr() of a torch CUDA tensor); *_host are host pointers.  The handle
+ *     owns only its packed copy of the sample set, small scratch and tables.
+ *   - every function returns 0 (SAA_OK) or a negative saa_status;
+ *     saa_last_error() gives the message.  No C++ exception crosses the ABI.
+ *   - a handle is not re-entrant: one host thread per handle; one process per
+ *     GPU for multi-GPU runs.  All device work is stream-ordered on `stream`
+ *     and asynchronous unless stated otherwise.
+ *   - precision: 64 -> all device buffers are double; 32 -> float (inputs to
+ *     saa_set_samples_* are always double in the reference layouts).
+ *
+ * QP variable order (reference drone/drone_risk.py:226,381): z = (u[0..n_u*S),
+ * y[0..M), slack, t).  Constraint-row order (drone_risk.py:282-374, :401-423):
+ *   [final rows (n_fin)] [CVaR row] [-y_i rows (M)] [sample rows (M*rows_per_sample)]
+ *   [-slack row] [control-bound rows (n_u*S)]            (method = SAA)
+ *   [final rows] [sample rows] [control-bound rows]       (method = BASELINE)
+ */
+#ifndef SAA_B200_H
+#define SAA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct saa_handle saa_handle;
+
+typedef enum {
+  SAA_OK = 0,
+  SAA_ERR_ARG = -1,        /* bad argument / unsupported configuration        */
+  SAA_ERR_CUDA = -2,       /* a CUDA runtime call failed                      */
+  SAA_ERR_STATE = -3,      /* call order violated (e.g. samples not set)      */
+  SAA_ERR_NO_DEVICE = -4   /* no usable CUDA device (there is NO CPU fallback)*/
+} saa_status;
+
+typedef enum { SAA_DRONE = 0, SAA_CAR = 1, SAA_HOPPER = 2 } saa_problem;
+typedef enum { SAA_METHOD_SAA = 0, SAA_METHOD_BASELINE = 1 } saa_method;
+/* drone only: drone_risk.py vs drone_times.py relaxation / baseline constants */
+typedef enum { SAA_VARIANT_RISK = 0, SAA_VARIANT_TIMES = 1 } saa_variant;
+
+int saa_version(void);
+/* message of the last failure on `h`; h == NULL -> last failure of saa_create */
+const char *saa_last_error(const saa_handle *h);
+
+/*
+ * Create a handle for `M_local` samples living on CUDA device `device`, being
+ * samples [sample_offset, sample_offset + M_local) of a global set of
+ * `M_global` (single GPU: M_local == M_global, sample_offset == 0).
+ * replaces: Model.__init__ (drone/drone_risk.py:70-93, car/driving.py:84-120,
+ *           hopper/hopper.py:90-104).
+ */
+int saa_create(saa_handle **out, int problem, int method, int variant,
+               int64_t M_local, int64_t M_global, int64_t sample_offset,
+               int S, double alpha, int precision, int device);
+int saa_destroy(saa_handle *h);
+
+/* ---- problem constants (the reference's params modules) ------------------- */
+typedef struct {               /* replaces: drone/drone_params.py:1-45        */
+  double dt, u_max, beta, drag_coefficient;
+  double gain_p, gain_v;       /* feedback_gain = -[gain_p I, gain_v I]       */
+  double x_init[6], x_final[6];
+  int32_t n_obs;               /* must be 3                                   */
+  double obs_positions[3][3];
+  double osqp_tol;             /* subtracted from Z_i in saa_cvar_terms       */
+} saa_drone_params;
+
+typedef struct {               /* replaces: car/driving_params.py:1-42        */
+  double dt, u_max, beta;      /* beta: car/driving.py:94                     */
+  double speed_ped_des, min_separation_distance;
+  double goal[4];              /* (position_ego_goal, velocity_ego_goal)      */
+  double osqp_tol;
+} saa_car_params;
+
+int saa_set_params_drone(saa_handle *h, const saa_drone_params *p);
+int saa_set_params_car(saa_handle *h, const saa_car_params *p);
+
+/* ---- sample sets (device pointers, reference array layouts, float64) ------
+ * The handle repacks them into its own structure-of-arrays layout (only the
+ * fields the path reads), so the caller may free its copies afterwards.       */
+/* replaces: drone_utils.sample_uncertain_parameters outputs handed to Model
+ * (drone/drone_utils.py:61-93): masses (M), DWs (M,S,6), obs_Qs (M,3,3,3);
+ * obs_Qs must be diagonal (only [.,o,0,0] and [.,o,1,1] are read).            */
+int saa_set_samples_drone(saa_handle *h, const double *masses_dev,
+                          const double *DWs_dev, const double *obs_Qs_dev,
+                          void *stream);
+/* replaces: car Model fields (car/driving.py:95-120): states_init (M,8),
+ * omegas_speed (M), omegas_repulsive (M), DWs (M,S,8).                        */
+int saa_set_samples_car(saa_handle *h, const double *states_init_dev,
+                        const double *omegas_speed_dev,
+                        const double *omegas_repulsive_dev,
+                        const double *DWs_dev, void *stream);
+
+/* ---- static CSC pattern of A for M_global samples (host, no GPU work) ------
+ * replaces: the pattern SciPy derives in sp.csr_matrix(dense) + sp.vstack(...,
+ * format='csc') (drone/drone_risk.py:419-420, car/driving.py:417-418).  It is
+ * structural (explicit zeros are kept).  `relaxed_pattern` != 0 gives the car's
+ * scp_iter == 0 pattern, where rows >= n_x were multiplied by exactly 0 and
+ * vanish (car/driving.py:411-415); ignored for the drone.                     */
+int saa_pattern_sizes(const saa_handle *h, int relaxed_pattern,
+                      int64_t *n_rows, int64_t *n_cols, int64_t *nnz);
+int saa_pattern_i32(const saa_handle *h, int relaxed_pattern,
+                    int32_t *indptr_host, int32_t *indices_host);
+int saa_pattern_i64(const saa_handle *h, int relaxed_pattern,
+                    int64_t *indptr_host, int64_t *indices_host);
+
+/* Same pattern without a handle (pure host arithmetic; usable on a machine
+ * without a GPU, e.g. by the process that owns the QP solver).               */
+int saa_static_pattern_sizes(int problem, int method, int S, int64_t M, int relaxed_pattern,
+                             int64_t *n_rows, int64_t *n_cols, int64_t *nnz);
+int saa_static_pattern_i32(int problem, int method, int S, int64_t M, int relaxed_pattern,
+                           int32_t *indptr_host, int32_t *indices_host);
+int saa_static_pattern_i64(int problem, int method, int S, int64_t M, int relaxed_pattern,
+                           int64_t *indptr_host, int64_t *indices_host);
+
+/*
+ * Where this rank's values go.  By default the destination is the GLOBAL
+ * matrix (M_out = M_global, first_out = sample_offset).  A rank may instead
+ * write a compact matrix of its own samples (M_out = M_local, first_out = 0).
+ * Ax/l/u pointers given to the calls below are the base of a matrix with M_out
+ * samples (they may be peer-mapped pointers to another GPU's buffer).
+ */
+int saa_set_output_geometry(saa_handle *h, int64_t M_out, int64_t first_out);
+
+/*
+ * Entries that do not depend on the iterate: y / slack / t columns, control
+ * identity, every lower bound, the constant upper bounds.  They depend only on
+ * whether the first-iteration relaxation is active (scp_iter below the
+ * problem's threshold), so call it once per (buffer, relaxation state).  Only
+ * this rank's sample slice of the per-sample constants is written, plus the
+ * O(1) shared entries if `write_shared` != 0 (one rank should do that).
+ * replaces: drone/drone_risk.py:221-237, :331-348, :360-368, :413-417;
+ *           car/driving.py:243-258, :334-366, :411-415.
+ */
+int saa_write_constants(saa_handle *h, int scp_iter, int write_shared,
+                        void *Ax_dev, void *l_dev, void *u_dev, void *stream);
+
+/*
+ * THE HOT PATH.  For every local sample: roll out the dynamics under the
+ * controls `us_host` (S*n_u values, row-major (S, n_u), always double),
+ * propagate the control sensitivities, evaluate the risk constraints, and
+ * write (a) the u-column entries of the sample rows straight into the CSC
+ * value array `Ax_dev`, (b) the sample rows' upper bounds into `u_dev`,
+ * (c) optionally Z_i = max_k g_ik into `Z_dev` (M_local values, may be NULL),
+ * (d) this rank's partial SUMS for the sample-mean rows into
+ * `mean_sums_dev` (saa_mean_len() doubles; always double).
+ * If `finalize` != 0 the sums are treated as global (single GPU), divided by
+ * M_global and scattered into Ax/l/u (same as saa_finalize_means).
+ * replaces: Model.get_all_constraints_coeffs_all + the relaxation of
+ * get_constraints_coeffs (drone/drone_risk.py:239-374, :413-417;
+ * car/driving.py:261-373, :411-415).
+ */
+int saa_linearize_assemble(saa_handle *h, const double *us_host, int scp_iter,
+                           void *Ax_dev, void *l_dev, void *u_dev, void *Z_dev,
+                           double *mean_sums_dev, int finalize, void *stream);
+int64_t saa_mean_len(const saa_handle *h);
+/* after an all-reduce(sum) of mean_sums over ranks: mean = sums / M_global ->
+ * final rows of Ax, l[0..n_fin), u[0..n_fin).
+ * replaces: jnp.mean(...) drone/drone_risk.py:294-300, car/driving.py:311-317 */
+int saa_finalize_means(saa_handle *h, const double *mean_sums_dev,
+                       void *Ax_dev, void *l_dev, void *u_dev, void *stream);
+
+/* Rollout only: Xs_dev (M_local, S+1, n_x) row-major.
+ * replaces: Model.us_to_state_trajectories (drone/drone_risk.py:157-162,
+ *           car/driving.py:207-214).                                          */
+int saa_rollout(saa_handle *h, const double *us_host, void *Xs_dev, void *stream);
+
+/*
+ * CVaR / Monte-Carlo terms.  Z_i = max_k g_ik - osqp_tol per local sample
+ * (written to Z_dev if not NULL), and into out3_dev (3 doubles, SUMS over the
+ * local samples): [ sum_i max(Z_i - t_risk, 0),  #{i : Z_i <= sat_tol},
+ * max_i Z_i ].  AV@R = t + out3[0] / (M_global * alpha) after an all-reduce.
+ * replaces: monte_carlo_*_verification and the closed form of monte_carlo_avar
+ * (drone/drone_risk.py:656-662, :694; car/driving.py:630-638, :670).          */
+int saa_cvar_terms(saa_handle *h, const double *us_host, double t_risk,
+                   double sat_tol, void *Z_dev, double *out3_dev, void *stream);
+
+/* ---- hopper slip-risk (hopper/hopper.py:300-367 and its derivatives) ------ */
+/* replaces: intensities/thetas/taus (hopper/hopper.py:68-74), each (M, n_feat)*/
+int saa_set_samples_hopper(saa_handle *h, int32_t n_features, double mu_nom,
+                           const double *intensities_dev, const double *thetas_dev,
+                           const double *taus_dev, void *stream);
+/*
+ * n_c contact instants with end-effector x positions px_host[c] and contact
+ * forces (fx_host[c], fz_host[c]).  Writes, per local sample i and contact c
+ * (index i*n_c + c):  mu_dev = mu_i(px_c),  dmu_dev = mu_i'(px_c).
+ * If lambda_dev != NULL (M_local*n_c multipliers) also the per-contact sums
+ * hess_sums_dev[2*c] = sum_i lambda_ic mu_i'(px_c), [2*c+1] = sum_i lambda_ic
+ * mu_i''(px_c)  (2*n_c doubles, local sums; all-reduce across ranks).
+ * replaces: friction_at_px under slip_risk_constraints and its jacrev /
+ * hessian (hopper/hopper.py:75-81, :300-367, :569-580).                       */
+int saa_hopper_friction(saa_handle *h, int32_t n_c, const double *px_host,
+                        void *mu_dev, void *dmu_dev, const double *lambda_dev,
+                        double *hess_sums_dev, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAA_B200_H */

@@ -1,0 +1,400 @@
+// Quadrotor SAA kernels (K1 assemble, K4 rollout, K5 CVaR terms), sm_100a.
+//
+// What is computed (reference drone/drone_risk.py):
+//   rollout            :139-155   x+ = x + dt b(x,u,m) + sqrt(dt) sigma dW
+//   constraints        :164-213   x_S - x_final ;  g[o,k] = 1 - (p_k-c_o)^T Q_o (p_k-c_o)
+//   per-sample Jacobian:239-280   jacfwd wrt us  (here: closed-form recursion)
+//   sample mean / pack :282-374
+//
+// The three axes decouple (diagonal feedback gain, per-axis drag), so the
+// Jacobian of the 6-state rollout is three independent 2x2 chains:
+//   p+ = p + dt v ;  v+ = v + dt (u - kp p - kd v - c|v|v)/m + noise
+//   d(p+,v+)/d(p,v) = [[1, dt], [a21, a22_k]],  a21 = -kp dt/m,
+//   a22_k = 1 - dt (kd + 2c|v_k|)/m,   d v+/du = dt/m.
+//
+// Thread mapping: one warp owns a tile of 16 samples; lanes 0-15 run the x axis
+// of those samples, lanes 16-31 the y axis (the z axis, which only feeds the
+// sample-mean rows, is split between the two lanes of a sample by an adjoint
+// pass).  For each control step j the lane runs the sensitivity chain
+// k = j+1..S in registers and stages the 3*(S-1-j) CSC entries of its sample
+// for column (j, axis) in shared memory; the warp then streams the two column
+// sub-runs (16 samples x 3*(S-1-j) contiguous doubles each) to global memory
+// with consecutive lanes on consecutive addresses.
+#pragma once
+#include "saa_common.cuh"
+
+namespace saa {
+
+template <int S> struct DroneRed {
+  static constexpr int FIN_P = 0;                 // + a*(S-1) + j   (a<3, j<S-1)
+  static constexpr int FIN_V = 3 * (S - 1);       // + a*S + j       (a<3, j<S)
+  static constexpr int VAL = FIN_V + 3 * S;       // + r             (r<6)
+  static constexpr int N = VAL + 6;
+};
+
+template <typename T, int S> struct DroneArgs {
+  const T *mass, *dw, *q;   // packed: mass[M]; dw[(k*3+a)*Mpad+s]; q[(o*2+a)*Mpad+s]
+  i64 M, Mpad;
+  T us[S * 3];
+  T dt, noise_c, drag, kp, kd;
+  T x0[6], xf[6];
+  T oc[3][2];
+  T escale;                 // multiplier (x relaxation scale) applied to the Jacobian entries
+  T ubscale, ubpad;         // upper bound = ubscale * (-g + grad g . u) - ubpad
+  T ztol;                   // Z_i = max g - ztol
+  T *Ax;
+  i64 col_off[2 * (S - 1)]; // [a*(S-1)+j]: offset in Ax of local sample 0's sub-run of column (j,a)
+  T *ub;                    // base of the upper-bound vector (nullptr: skip)
+  i64 ub_off;               // row of local sample 0's first sample row
+  T *Z;                     // per-sample max constraint (nullptr: skip)
+  double *partials;         // [gridDim.x][DroneRed<S>::N]
+};
+
+// ---- one sensitivity chain: column (j, axis) --------------------------------
+template <typename T, int S, int J> struct DroneChain {
+  static constexpr int L = S - 1 - J;      // rows k = J+2..S carry an entry
+  static constexpr int LEN = 3 * L;        // per-sample run length in the CSC column
+  static constexpr int STRIDE = LEN | 1;   // odd stride: conflict-free staging
+};
+
+template <typename T, int S, int J>
+__device__ __forceinline__ void drone_chain(const T (&P)[S + 1], const T (&A22)[S],
+                                            const T (&q2)[3], const T (&oca)[3],
+                                            T dt, T a21, T dtm, T *stage_mine,
+                                            T &sp_out, T &sv_out) {
+  using C = DroneChain<T, S, J>;
+  T q2j[3] = {q2[0], q2[1], q2[2]};
+  T ocj[3] = {oca[0], oca[1], oca[2]};
+  // recompute the coefficients per chain: registers over flops
+  opaque(q2j[0]); opaque(q2j[1]); opaque(q2j[2]);
+  opaque(ocj[0]); opaque(ocj[1]); opaque(ocj[2]);
+  T sp = T(0), sv = dtm;                   // d(p,v)_{J+1} / du_J
+#pragma unroll
+  for (int k = J + 1; k < S; ++k) {
+    const T nsp = fma(dt, sv, sp);
+    const T nsv = fma(A22[k], sv, a21 * sp);
+    sp = nsp; sv = nsv;                    // now d(p,v)_{k+1} / du_J
+    const int kk = k - J - 1;              // row (k+1) is the kk-th row of this column's run
+#pragma unroll
+    for (int o = 0; o < 3; ++o) {
+      const T coef = q2j[o] * (P[k + 1] - ocj[o]);   // escale * d g[o,k+1] / d p
+      stage_mine[o * C::L + kk] = coef * sp;
+    }
+  }
+  sp_out = sp; sv_out = sv;
+}
+
+template <typename T, int S, int WARPS>
+struct DroneSmem {
+  static constexpr int STAGE = 2 * kTileSamples * (3 * (S - 1));   // elements per warp
+  T stage[WARPS][STAGE];
+  double wacc[WARPS][DroneRed<S>::N];
+};
+
+template <typename T, int S, int J>
+__device__ __forceinline__ void drone_chain_loop(const DroneArgs<T, S> &A, const T (&P)[S + 1],
+                                                 const T (&A22)[S], const T (&q2)[3],
+                                                 const T (&oca)[3], T a21, T dtm, T *stage,
+                                                 double *wacc, int a, int si, int lane, i64 s0,
+                                                 int ns, bool active) {
+  using Rd = DroneRed<S>;
+  if constexpr (J == S - 1) {
+    // last control step: no sample rows, only d v_S/du = dt/m in the mean rows
+    const double rv = sum16((double)(active ? dtm : T(0)));
+    if (si == 0) wacc[Rd::FIN_V + a * S + (S - 1)] += rv;
+  } else {
+    using C = DroneChain<T, S, J>;
+    T sp, sv;
+    T *mine = stage + (a * kTileSamples + si) * C::STRIDE;
+    drone_chain<T, S, J>(P, A22, q2, oca, A.dt, a21, dtm, mine, sp, sv);
+    // sample-mean rows: d p_S / du_J and d v_S / du_J summed over the tile
+    const double rp = sum16((double)(active ? sp : T(0)));
+    const double rv = sum16((double)(active ? sv : T(0)));
+    if (si == 0) {
+      wacc[Rd::FIN_P + a * (S - 1) + J] += rp;
+      wacc[Rd::FIN_V + a * S + J] += rv;
+    }
+    __syncwarp();
+    const int n = ns * C::LEN;
+    i64 base = s0 * C::LEN;
+    opaque(base);   // keep the 2(S-1) column bases in the constant bank, not hoisted into registers
+    copy_run<T, C::LEN, C::STRIDE>(A.Ax + (A.col_off[J] + base), stage, n, lane);
+    copy_run<T, C::LEN, C::STRIDE>(A.Ax + (A.col_off[(S - 1) + J] + base),
+                                   stage + kTileSamples * C::STRIDE, n, lane);
+    __syncwarp();
+    drone_chain_loop<T, S, J + 1>(A, P, A22, q2, oca, a21, dtm, stage, wacc, a, si, lane, s0, ns,
+                                  active);
+  }
+}
+
+// ---- K1: linearize + assemble ------------------------------------------------
+template <typename T, int S, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 2)
+drone_assemble_kernel(const __grid_constant__ DroneArgs<T, S> A) {
+  using Rd = DroneRed<S>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  auto &sm = *reinterpret_cast<DroneSmem<T, S, WARPS> *>(smem_raw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int a = lane >> 4, si = lane & 15;
+  T *stage = sm.stage[warp];
+  double *wacc = sm.wacc[warp];
+  for (int r = lane; r < Rd::N; r += 32) wacc[r] = 0.0;
+  __syncwarp();
+
+  const i64 ntiles = (A.M + kTileSamples - 1) / kTileSamples;
+  for (i64 tile = (i64)blockIdx.x * WARPS + warp; tile < ntiles; tile += (i64)gridDim.x * WARPS) {
+    const i64 s0 = tile * kTileSamples;
+    const int ns = (int)min((i64)kTileSamples, A.M - s0);
+    const bool active = si < ns;
+    const i64 s = s0 + (active ? si : 0);
+    const T inv_m = T(1) / A.mass[s];
+    const T dt = A.dt, dtm = dt * inv_m, a21 = -A.kp * dtm;
+    const T nz = A.noise_c * inv_m;
+    const T c2 = T(2) * A.drag;
+
+    // ---------------- z axis: feeds only the sample-mean rows -----------------
+    {
+      T a22z[S];
+      T p = A.x0[2], v = A.x0[5], tp = T(0), tv = T(0);
+#pragma unroll
+      for (int k = 0; k < S; ++k) {
+        const T absv = fabs(v);
+        const T a22 = T(1) - dtm * (A.kd + c2 * absv);
+        a22z[k] = a22;
+        const T u = A.us[k * 3 + 2];
+        const T acc = (u - A.kp * p - A.kd * v - A.drag * absv * v) * inv_m;
+        const T ntp = fma(dt, tv, tp);
+        const T ntv = fma(a22, tv, fma(a21, tp, dtm * u));
+        const T np_ = fma(dt, v, p);
+        v = v + dt * acc + nz * A.dw[(k * 3 + 2) * A.Mpad + s];
+        p = np_; tp = ntp; tv = ntv;
+      }
+      // linearisation offset of the final rows: -(x_S - x_f) + d x_S/du . u  (:271)
+      const T valz = (a == 0) ? (-(p - A.xf[2]) + tp) : (-(v - A.xf[5]) + tv);
+      const double rz = sum16((double)(active ? valz : T(0)));
+      if (si == 0) wacc[Rd::VAL + (a == 0 ? 2 : 5)] += rz;
+      // adjoint pass: lane a=0 carries e_p (row p_z), lane a=1 carries e_v (row v_z)
+      T lp = (a == 0) ? T(1) : T(0), lv = (a == 0) ? T(0) : T(1);
+#pragma unroll
+      for (int j = S - 1; j >= 0; --j) {
+        const double r = sum16((double)(active ? lv * dtm : T(0)));
+        if (si == 0) {
+          if (a == 1) wacc[Rd::FIN_V + 2 * S + j] += r;
+          else if (j < S - 1) wacc[Rd::FIN_P + 2 * (S - 1) + j] += r;
+        }
+        const T nlp = fma(a21, lv, lp);
+        const T nlv = fma(a22z[j], lv, dt * lp);
+        lp = nlp; lv = nlv;
+      }
+    }
+
+    // ---------------- own axis (x or y): rollout + constraint values ----------
+    T P[S + 1], A22[S];
+    T q[3], q2[3], oca[3];
+#pragma unroll
+    for (int o = 0; o < 3; ++o) {
+      q[o] = A.q[(o * 2 + a) * A.Mpad + s];
+      q2[o] = T(-2) * A.escale * q[o];
+      oca[o] = a ? A.oc[o][1] : A.oc[o][0];
+    }
+    {
+      T p = a ? A.x0[1] : A.x0[0], v = a ? A.x0[4] : A.x0[3], tp = T(0), tv = T(0);
+      T zmax = -INFINITY;
+      P[0] = p;
+#pragma unroll
+      for (int k = 0; k < S; ++k) {
+        const T absv = fabs(v);
+        const T a22 = T(1) - dtm * (A.kd + c2 * absv);
+        A22[k] = a22;
+        const T u = a ? A.us[k * 3 + 1] : A.us[k * 3];
+        const T acc = (u - A.kp * p - A.kd * v - A.drag * absv * v) * inv_m;
+        const T ntp = fma(dt, tv, tp);
+        const T ntv = fma(a22, tv, fma(a21, tp, dtm * u));
+        const T np_ = fma(dt, v, p);
+        v = v + dt * acc + nz * A.dw[(k * 3 + a) * A.Mpad + s];
+        p = np_; tp = ntp; tv = ntv;
+        P[k + 1] = p;
+#pragma unroll
+        for (int o = 0; o < 3; ++o) {
+          const T d = p - oca[o];
+          const T w = q[o] * d * d;                       // own-axis part of 1 - g
+          const T e = fma(T(-2) * q[o] * d, tp, w);       // own-axis part of 1 - g + grad g . u
+          const T wsum = w + __shfl_xor_sync(0xffffffffu, w, 16);
+          const T esum = e + __shfl_xor_sync(0xffffffffu, e, 16);
+          zmax = fmax(zmax, T(1) - wsum);
+          if (a == (k & 1))                               // the two lanes of a sample share the stores
+            stage[si * (3 * S + 1) + o * S + k] = fma(esum - T(1), A.ubscale, -A.ubpad);
+        }
+      }
+      const T valp = -(p - (a ? A.xf[1] : A.xf[0])) + tp, valv = -(v - (a ? A.xf[4] : A.xf[3])) + tv;
+      const double rp = sum16((double)(active ? valp : T(0)));
+      const double rv = sum16((double)(active ? valv : T(0)));
+      if (si == 0) { wacc[Rd::VAL + a] += rp; wacc[Rd::VAL + 3 + a] += rv; }
+      if (A.Z != nullptr && a == 0 && active) A.Z[s] = zmax - A.ztol;
+      __syncwarp();
+      if (A.ub != nullptr)
+        copy_run<T, 3 * S, 3 * S + 1>(A.ub + A.ub_off + s0 * (3 * S), stage, ns * 3 * S, lane);
+      __syncwarp();
+    }
+
+    // ---------------- sensitivity chains, one CSC column pair per control step -
+    drone_chain_loop<T, S, 0>(A, P, A22, q2, oca, a21, dtm, stage, wacc, a, si, lane, s0, ns,
+                              active);
+  }
+
+  // ---------------- per-block partial sums (fixed order => deterministic) -----
+  __syncthreads();
+  for (int r = threadIdx.x; r < Rd::N; r += WARPS * 32) {
+    double acc = 0.0;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) acc += sm.wacc[w][r];
+    A.partials[(i64)blockIdx.x * Rd::N + r] = acc;
+  }
+}
+
+// ---- finalize: sum block partials in block order, divide, scatter ------------
+// sums_out (optional): the plain sums, for the multi-GPU all-reduce.
+template <typename T>
+__global__ void reduce_partials_kernel(const double *__restrict__ partials, int nblocks, int n,
+                                       double *__restrict__ sums_out) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  double acc = 0.0;
+  for (int b = 0; b < nblocks; ++b) acc += partials[(i64)b * n + r];
+  sums_out[r] = acc;
+}
+
+template <typename T>
+__global__ void scatter_means_kernel(const double *__restrict__ sums, double inv_M, int n_entries,
+                                     const i64 *__restrict__ fin_off, int n_fin, T *Ax, T *l,
+                                     T *u) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n_entries) {
+    Ax[fin_off[r]] = (T)(sums[r] * inv_M);
+  } else if (r < n_entries + n_fin) {
+    const T v = (T)(sums[r] * inv_M);
+    l[r - n_entries] = v;          // equality by equal bounds (:272-273)
+    u[r - n_entries] = v;
+  }
+}
+
+// ---- K4 / K5: rollout only, optional trajectory output and CVaR terms --------
+template <typename T, int S> struct DroneRollArgs {
+  const T *mass, *dw, *q;
+  i64 M, Mpad;
+  T us[S * 3];
+  T dt, noise_c, drag, kp, kd;
+  T x0[6];
+  T oc[3][2];
+  T *Xs;            // (M, S+1, 6) or nullptr
+  T *Z;             // (M) or nullptr
+  T ztol, t_risk, sat_tol;
+  double *partials; // [gridDim.x][3] or nullptr: sum max(Z-t,0), count Z<=sat_tol, max Z
+};
+
+// one thread per sample; trajectories are staged per warp so that the
+// (S+1)*6 contiguous doubles of each sample leave as full coalesced runs.
+template <typename T, int S, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+drone_rollout_kernel(const __grid_constant__ DroneRollArgs<T, S> A) {
+  constexpr int ROW = (S + 1) * 6, STRIDE = ROW | 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T *stage = reinterpret_cast<T *>(smem_raw) + (threadIdx.x >> 5) * 32 * STRIDE;
+  __shared__ double red[WARPS][3];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double acc_excess = 0.0, acc_sat = 0.0, acc_max = -INFINITY;
+  const i64 ntiles = (A.M + 31) / 32;
+  for (i64 tile = (i64)blockIdx.x * WARPS + warp; tile < ntiles; tile += (i64)gridDim.x * WARPS) {
+    const i64 s0 = tile * 32;
+    const int ns = (int)min((i64)32, A.M - s0);
+    const bool active = lane < ns;
+    const i64 s = s0 + (active ? lane : 0);
+    const T inv_m = T(1) / A.mass[s];
+    const T dt = A.dt, nz = A.noise_c * inv_m;
+    T p[3], v[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { p[a] = A.x0[a]; v[a] = A.x0[3 + a]; }
+    T qx[3], qy[3];
+#pragma unroll
+    for (int o = 0; o < 3; ++o) { qx[o] = A.q[(o * 2) * A.Mpad + s]; qy[o] = A.q[(o * 2 + 1) * A.Mpad + s]; }
+    T zmax = -INFINITY;
+    T *mine = stage + lane * STRIDE;
+    if (A.Xs != nullptr) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) { mine[a] = p[a]; mine[3 + a] = v[a]; }
+    }
+#pragma unroll
+    for (int k = 0; k < S; ++k) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const T absv = fabs(v[a]);
+        const T acc = (A.us[k * 3 + a] - A.kp * p[a] - A.kd * v[a] - A.drag * absv * v[a]) * inv_m;
+        const T np_ = fma(dt, v[a], p[a]);
+        v[a] = v[a] + dt * acc + nz * A.dw[(k * 3 + a) * A.Mpad + s];
+        p[a] = np_;
+      }
+      if (A.Xs != nullptr) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { mine[(k + 1) * 6 + a] = p[a]; mine[(k + 1) * 6 + 3 + a] = v[a]; }
+      }
+#pragma unroll
+      for (int o = 0; o < 3; ++o) {
+        const T dx = p[0] - A.oc[o][0], dy = p[1] - A.oc[o][1];
+        zmax = fmax(zmax, T(1) - (qx[o] * dx * dx + qy[o] * dy * dy));
+      }
+    }
+    const T Zi = zmax - A.ztol;
+    if (A.Z != nullptr && active) A.Z[s] = Zi;
+    if (active) {
+      acc_excess += (double)fmax(Zi - A.t_risk, T(0));
+      acc_sat += (Zi <= A.sat_tol) ? 1.0 : 0.0;
+      acc_max = fmax(acc_max, (double)Zi);
+    }
+    if (A.Xs != nullptr) {
+      __syncwarp();
+      copy_run<T, ROW, STRIDE>(A.Xs + s0 * ROW, stage, ns * ROW, lane);
+      __syncwarp();
+    }
+  }
+  if (A.partials != nullptr) {
+    acc_excess = sum32(acc_excess); acc_sat = sum32(acc_sat); acc_max = max32(acc_max);
+    if (lane == 0) { red[warp][0] = acc_excess; red[warp][1] = acc_sat; red[warp][2] = acc_max; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double e = 0.0, c = 0.0, m = -INFINITY;
+      for (int w = 0; w < WARPS; ++w) { e += red[w][0]; c += red[w][1]; m = fmax(m, red[w][2]); }
+      A.partials[(i64)blockIdx.x * 3 + 0] = e;
+      A.partials[(i64)blockIdx.x * 3 + 1] = c;
+      A.partials[(i64)blockIdx.x * 3 + 2] = m;
+    }
+  }
+}
+
+// out3 = [sum excess, count satisfied, max Z] over blocks, fixed order
+__global__ void reduce_cvar_kernel(const double *__restrict__ partials, int nblocks,
+                                   double *__restrict__ out3) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double e = 0.0, c = 0.0, m = -INFINITY;
+    for (int b = 0; b < nblocks; ++b) {
+      e += partials[b * 3]; c += partials[b * 3 + 1]; m = fmax(m, partials[b * 3 + 2]);
+    }
+    out3[0] = e; out3[1] = c; out3[2] = m;
+  }
+}
+
+// ---- repack the reference-layout sample set into the kernel's SoA layout -----
+template <typename T>
+__global__ void drone_pack_kernel(const double *__restrict__ masses, const double *__restrict__ DWs,
+                                  const double *__restrict__ obs_Qs, i64 M, i64 Mpad, int S, T *mass,
+                                  T *dw, T *q) {
+  const i64 s = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= Mpad) return;
+  const i64 src = s < M ? s : M - 1;     // pad with a valid sample (never written out)
+  mass[s] = (T)masses[src];
+  for (int k = 0; k < S; ++k)
+    for (int a = 0; a < 3; ++a) dw[(k * 3 + a) * Mpad + s] = (T)DWs[(src * S + k) * 6 + 3 + a];
+  for (int o = 0; o < 3; ++o)
+    for (int a = 0; a < 2; ++a) q[(o * 2 + a) * Mpad + s] = (T)obs_Qs[((src * 3 + o) * 3 + a) * 3 + a];
+}
+
+}  // namespace saa

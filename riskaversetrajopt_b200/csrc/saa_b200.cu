@@ -1,0 +1,563 @@
+// libsaa_b200.so -- C ABI implementation (see include/saa_b200.h).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+
+#include "saa_common.cuh"
+#include "layout.cuh"
+#include "drone_kernels.cuh"
+#include "car_kernels.cuh"
+#include "hopper_kernels.cuh"
+
+using namespace saa;
+
+namespace {
+
+constexpr int kVersion = 100;
+constexpr int kS = 20;            // horizon the kernels are instantiated for (reference: S = 20)
+constexpr int kWarps = 6;         // warps per block of the assemble kernels (2 blocks / SM)
+constexpr int kBlocksPerSM = 2;
+
+thread_local std::string g_create_error;
+
+}  // namespace
+
+struct saa_handle {
+  int problem = 0, method = 0, variant = 0, S = 0, precision = 64, device = 0;
+  i64 M_local = 0, M_global = 0, sample_offset = 0;
+  i64 M_out = 0, first_out = 0;
+  double alpha = 0.1;
+  bool params_set = false, samples_set = false;
+  saa_drone_params dp{};
+  saa_car_params cp{};
+  // packed samples (device, library-owned)
+  i64 Mpad = 0;
+  void *d_a = nullptr, *d_b = nullptr, *d_c = nullptr, *d_d = nullptr;
+  // hopper
+  int n_feat = 0; double mu_nom = 0.0;
+  // scratch
+  int n_sms = kSMs;
+  double *d_partials = nullptr; i64 partials_len = 0;
+  double *d_sums = nullptr;
+  i64 *d_fin_off = nullptr;
+  Layout lay;                 // destination geometry (M_out)
+  mutable std::string err;
+};
+
+namespace {
+
+int fail(const saa_handle *h, int code, const std::string &msg) {
+  if (h) h->err = msg; else g_create_error = msg;
+  return code;
+}
+#define SAA_CUDA(h, call)                                                              \
+  do {                                                                                 \
+    cudaError_t e_ = (call);                                                           \
+    if (e_ != cudaSuccess)                                                             \
+      return fail(h, SAA_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+size_t esize(const saa_handle *h) { return h->precision == 64 ? 8 : 4; }
+
+int relax_threshold(const saa_handle *h) { return h->problem == SAA_DRONE ? 2 : 1; }
+
+// relaxation constants of get_constraints_coeffs (drone_risk.py:413-417, drone_times.py:421-425)
+void drone_relax(const saa_handle *h, double *scale, double *bound) {
+  if (h->variant == SAA_VARIANT_TIMES) { *scale = 1e-5; *bound = 10.0; }
+  else { *scale = 1e-7; *bound = 0.1; }
+}
+// multiplier / padding of the sample rows (drone_risk.py:310, :324-325, :352; drone_times.py:324-334)
+void drone_mult(const saa_handle *h, double *mult, double *pad) {
+  if (h->method == SAA_METHOD_BASELINE) {
+    if (h->variant == SAA_VARIANT_TIMES) { *mult = 1.0; *pad = 0.0; }
+    else { *mult = 0.01; *pad = 1e-3; }
+  } else { *mult = 0.01; *pad = 0.0; }
+}
+
+int ensure_scratch(saa_handle *h, i64 partial_doubles) {
+  if (h->partials_len < partial_doubles) {
+    if (h->d_partials) cudaFree(h->d_partials);
+    h->d_partials = nullptr; h->partials_len = 0;
+    SAA_CUDA(h, cudaMalloc(&h->d_partials, partial_doubles * sizeof(double)));
+    h->partials_len = partial_doubles;
+  }
+  if (!h->d_sums) SAA_CUDA(h, cudaMalloc(&h->d_sums, 1024 * sizeof(double)));
+  return SAA_OK;
+}
+
+// offsets (in the destination Ax) of the sample-mean entries, in the order of
+// the kernels' reduction slots
+int upload_fin_offsets(saa_handle *h) {
+  std::vector<i64> off;
+  const Layout &L = h->lay;
+  const int S = h->S;
+  int rows[4];
+  auto pos = [&](int c, int row) -> i64 {
+    const int n = L.fin_rows(c, rows);
+    for (int r = 0; r < n; ++r) if (rows[r] == row) return L.ucol[c] + r;
+    return -1;
+  };
+  if (h->problem == SAA_DRONE) {
+    for (int a = 0; a < 3; ++a) for (int j = 0; j < S - 1; ++j) off.push_back(pos(j * 3 + a, a));
+    for (int a = 0; a < 3; ++a) for (int j = 0; j < S; ++j) off.push_back(pos(j * 3 + a, 3 + a));
+  } else {
+    // car slots: CarRed: PX (c<2, j<S-1), PY (c<2, j<S-1), V (j<S), PHI (j<S)
+    for (int c = 0; c < 2; ++c) for (int j = 0; j < S - 1; ++j) off.push_back(pos(j * 2 + c, 0));
+    for (int c = 0; c < 2; ++c) for (int j = 0; j < S - 1; ++j) off.push_back(pos(j * 2 + c, 1));
+    for (int j = 0; j < S; ++j) off.push_back(pos(j * 2 + 0, 2));
+    for (int j = 0; j < S; ++j) off.push_back(pos(j * 2 + 1, 3));
+  }
+  for (i64 o : off) if (o < 0) return fail(h, SAA_ERR_STATE, "internal: final-row offset");
+  if (!h->d_fin_off) SAA_CUDA(h, cudaMalloc(&h->d_fin_off, 256 * sizeof(i64)));
+  SAA_CUDA(h, cudaMemcpy(h->d_fin_off, off.data(), off.size() * sizeof(i64), cudaMemcpyHostToDevice));
+  return SAA_OK;
+}
+
+int set_geometry(saa_handle *h, i64 M_out, i64 first_out) {
+  if (M_out < h->M_local || first_out < 0 || first_out + h->M_local > M_out)
+    return fail(h, SAA_ERR_ARG, "output geometry does not contain the local samples");
+  h->M_out = M_out; h->first_out = first_out;
+  h->lay.build(h->problem, h->method, h->S, M_out, false);
+  if (h->problem != SAA_HOPPER) return upload_fin_offsets(h);
+  return SAA_OK;
+}
+
+// ---------------------------------------------------------------------------
+// constants kernel (generic over drone / car)
+// ---------------------------------------------------------------------------
+struct ConstArgs {
+  i64 M_local, first_out, M_out;
+  int R, nu, n_fin;
+  int saa;                 // method == SAA
+  int write_shared;
+  i64 ycol0, ycol_len, slackcol, tcol;
+  i64 row_cvar, row_y0, row_s0, row_slack, row_ctrl0;
+  double cvar_y, cvar_slack, cvar_t, y_diag, y_slack, y_rows, t_rows, slack_last;
+  double l_rows, u_cvar, u_y, u_slack;      // bounds of the risk rows
+  int write_u_rows; double u_rows;          // relaxed: sample-row upper bounds are constant
+  double u_max;
+  i64 ucol_last[64];                        // position of the control-identity entry per u column
+};
+
+template <typename T>
+__global__ void write_constants_kernel(const __grid_constant__ ConstArgs C, T *Ax, T *l, T *u) {
+  const i64 tid = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  const i64 nth = (i64)gridDim.x * blockDim.x;
+  const i64 n_samp_rows = C.M_local * C.R;
+  // per-sample-row constants
+  for (i64 e = tid; e < n_samp_rows; e += nth) {
+    const i64 grow = C.first_out * C.R + e;           // sample-row index in the destination
+    l[C.row_s0 + grow] = (T)C.l_rows;
+    if (C.write_u_rows) u[C.row_s0 + grow] = (T)C.u_rows;
+    if (C.saa) {
+      Ax[C.tcol + 1 + grow] = (T)C.t_rows;
+      const i64 i = e / C.R, r = e - i * C.R;
+      Ax[C.ycol0 + (C.first_out + i) * C.ycol_len + 2 + r] = (T)C.y_rows;
+    }
+  }
+  if (C.saa) {
+    for (i64 i = tid; i < C.M_local; i += nth) {
+      const i64 gi = C.first_out + i;
+      Ax[C.ycol0 + gi * C.ycol_len] = (T)C.cvar_y;
+      Ax[C.ycol0 + gi * C.ycol_len + 1] = (T)C.y_diag;
+      Ax[C.slackcol + 1 + gi] = (T)C.y_slack;
+      l[C.row_y0 + gi] = (T)C.l_rows;
+      u[C.row_y0 + gi] = (T)C.u_y;
+    }
+  }
+  if (C.write_shared && tid < C.nu) {
+    Ax[C.ucol_last[tid]] = (T)1.0;
+    l[C.row_ctrl0 + tid] = (T)(-C.u_max);
+    u[C.row_ctrl0 + tid] = (T)C.u_max;
+  }
+  if (C.write_shared && C.saa && tid == 0) {
+    Ax[C.slackcol] = (T)C.cvar_slack;
+    Ax[C.slackcol + 1 + C.M_out] = (T)C.slack_last;
+    Ax[C.tcol] = (T)C.cvar_t;
+    l[C.row_cvar] = (T)C.l_rows; u[C.row_cvar] = (T)C.u_cvar;
+    l[C.row_slack] = (T)C.l_rows; u[C.row_slack] = (T)C.u_slack;
+  }
+}
+
+template <typename T>
+int launch_constants(saa_handle *h, int scp_iter, int write_shared, void *Ax, void *l, void *u,
+                     cudaStream_t st) {
+  const Layout &L = h->lay;
+  if (L.nu > 64) return fail(h, SAA_ERR_ARG, "n_u*S > 64 unsupported");
+  ConstArgs C{};
+  C.M_local = h->M_local; C.first_out = h->first_out; C.M_out = h->M_out;
+  C.R = L.R; C.nu = L.nu; C.n_fin = L.n_fin;
+  C.saa = h->method == SAA_METHOD_SAA;
+  C.write_shared = write_shared;
+  C.ycol0 = L.ycol0; C.ycol_len = L.ycol_len(); C.slackcol = L.slackcol; C.tcol = L.tcol;
+  C.row_cvar = L.row_cvar; C.row_y0 = L.row_y0; C.row_s0 = L.row_s0; C.row_slack = L.row_slack;
+  C.row_ctrl0 = L.row_ctrl0;
+  const bool relaxed = scp_iter < relax_threshold(h);
+  const double inf = std::numeric_limits<double>::infinity();
+  double mult = 1.0, pad = 0.0, scale = 1.0, bound = 0.0;
+  if (h->problem == SAA_DRONE) { drone_mult(h, &mult, &pad); drone_relax(h, &scale, &bound); }
+  if (h->problem == SAA_CAR && relaxed)
+    return fail(h, SAA_ERR_ARG, "car scp_iter == 0 uses the relaxed pattern: call saa_car_relaxed");
+  const double rs = relaxed ? scale : 1.0;
+  C.cvar_y = 1.0 * rs; C.cvar_slack = 1.0 * rs;               // slack gets 1.0: fill slice quirk (:337)
+  C.cvar_t = (double)h->M_global * h->alpha * rs;
+  C.y_diag = -1.0 * rs; C.y_slack = -1.0 * rs; C.slack_last = -1.0 * rs;
+  C.y_rows = -mult * rs; C.t_rows = -mult * rs;
+  C.l_rows = relaxed ? -bound : -inf;
+  C.u_cvar = C.u_y = C.u_slack = relaxed ? bound : 0.0;
+  C.write_u_rows = relaxed; C.u_rows = bound;
+  C.u_max = h->problem == SAA_DRONE ? h->dp.u_max : h->cp.u_max;
+  for (int c = 0; c < L.nu; ++c) C.ucol_last[c] = L.ucol[c + 1] - 1;
+  const i64 work = std::max<i64>(h->M_local * L.R, 64);
+  const int threads = 256;
+  const int blocks = (int)std::min<i64>((work + threads - 1) / threads, (i64)h->n_sms * 8);
+  write_constants_kernel<T><<<blocks, threads, 0, st>>>(C, (T *)Ax, (T *)l, (T *)u);
+  SAA_CUDA(h, cudaGetLastError());
+  return SAA_OK;
+}
+
+// ---------------------------------------------------------------------------
+// drone launchers
+// ---------------------------------------------------------------------------
+template <typename T>
+void fill_drone_common(const saa_handle *h, const double *us, T *us_out, T &dt, T &noise_c, T &drag,
+                       T &kp, T &kd, T (&x0)[6], T (&oc)[3][2]) {
+  for (int i = 0; i < kS * 3; ++i) us_out[i] = (T)us[i];
+  dt = (T)h->dp.dt;
+  noise_c = (T)(std::sqrt(h->dp.dt) * h->dp.beta);
+  drag = (T)h->dp.drag_coefficient; kp = (T)h->dp.gain_p; kd = (T)h->dp.gain_v;
+  for (int i = 0; i < 6; ++i) x0[i] = (T)h->dp.x_init[i];
+  for (int o = 0; o < 3; ++o) for (int a = 0; a < 2; ++a) oc[o][a] = (T)h->dp.obs_positions[o][a];
+}
+
+int grid_for(const saa_handle *h, i64 ntiles, int warps, int blocks_per_sm) {
+  const i64 want = (ntiles + warps - 1) / warps;
+  return (int)std::max<i64>(1, std::min<i64>(want, (i64)h->n_sms * blocks_per_sm));
+}
+
+template <typename T>
+int launch_drone_assemble(saa_handle *h, const double *us, int scp_iter, void *Ax, void *u, void *Z,
+                          int *grid_out, cudaStream_t st) {
+  using Args = DroneArgs<T, kS>;
+  using Smem = DroneSmem<T, kS, kWarps>;
+  Args A{};
+  A.mass = (const T *)h->d_a; A.dw = (const T *)h->d_b; A.q = (const T *)h->d_c;
+  A.M = h->M_local; A.Mpad = h->Mpad;
+  fill_drone_common<T>(h, us, A.us, A.dt, A.noise_c, A.drag, A.kp, A.kd, A.x0, A.oc);
+  for (int i = 0; i < 6; ++i) A.xf[i] = (T)h->dp.x_final[i];
+  double mult, pad, scale, bound;
+  drone_mult(h, &mult, &pad); drone_relax(h, &scale, &bound);
+  const bool relaxed = scp_iter < 2;
+  A.escale = (T)(relaxed ? mult * scale : mult);
+  A.ubscale = (T)mult; A.ubpad = (T)pad; A.ztol = (T)0;
+  A.Ax = (T *)Ax;
+  const Layout &L = h->lay;
+  for (int a = 0; a < 2; ++a)
+    for (int j = 0; j < kS - 1; ++j) {
+      const int c = j * 3 + a;
+      A.col_off[a * (kS - 1) + j] = L.run_start(c) + h->first_out * L.run_len(c);
+    }
+  A.ub = relaxed ? nullptr : (T *)u;          // relaxed: bounds are the constant +-bound
+  A.ub_off = L.row_s0 + h->first_out * L.R;
+  A.Z = (T *)Z;
+  const i64 ntiles = (h->M_local + kTileSamples - 1) / kTileSamples;
+  const int grid = grid_for(h, ntiles, kWarps, kBlocksPerSM);
+  int rc = ensure_scratch(h, (i64)grid * DroneRed<kS>::N);
+  if (rc) return rc;
+  A.partials = h->d_partials;
+  auto kern = drone_assemble_kernel<T, kS, kWarps>;
+  SAA_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+  kern<<<grid, kWarps * 32, sizeof(Smem), st>>>(A);
+  SAA_CUDA(h, cudaGetLastError());
+  *grid_out = grid;
+  return SAA_OK;
+}
+
+template <typename T>
+int launch_drone_rollout(saa_handle *h, const double *us, void *Xs, void *Z, double t_risk,
+                         double sat_tol, double ztol, double *out3, cudaStream_t st) {
+  constexpr int W = 4;
+  using Args = DroneRollArgs<T, kS>;
+  Args A{};
+  A.mass = (const T *)h->d_a; A.dw = (const T *)h->d_b; A.q = (const T *)h->d_c;
+  A.M = h->M_local; A.Mpad = h->Mpad;
+  fill_drone_common<T>(h, us, A.us, A.dt, A.noise_c, A.drag, A.kp, A.kd, A.x0, A.oc);
+  A.Xs = (T *)Xs; A.Z = (T *)Z;
+  A.ztol = (T)ztol; A.t_risk = (T)t_risk; A.sat_tol = (T)sat_tol;
+  const i64 ntiles = (h->M_local + 31) / 32;
+  const int grid = grid_for(h, ntiles, W, 4);
+  int rc = ensure_scratch(h, (i64)grid * 3);
+  if (rc) return rc;
+  A.partials = out3 ? h->d_partials : nullptr;
+  const size_t smem = Xs ? (size_t)W * 32 * (((kS + 1) * 6) | 1) * sizeof(T) : 0;
+  auto kern = drone_rollout_kernel<T, kS, W>;
+  SAA_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(W * 32 * (((kS + 1) * 6) | 1) * sizeof(T))));
+  kern<<<grid, W * 32, smem, st>>>(A);
+  SAA_CUDA(h, cudaGetLastError());
+  if (out3) {
+    reduce_cvar_kernel<<<1, 32, 0, st>>>(h->d_partials, grid, out3);
+    SAA_CUDA(h, cudaGetLastError());
+  }
+  return SAA_OK;
+}
+
+template <typename T>
+int launch_finalize(saa_handle *h, const double *sums, void *Ax, void *l, void *u, cudaStream_t st) {
+  const int n_entries = (int)saa_mean_len(h) - h->lay.n_fin;
+  const int n = n_entries + h->lay.n_fin;
+  scatter_means_kernel<T><<<(n + 127) / 128, 128, 0, st>>>(sums, 1.0 / (double)h->M_global, n_entries,
+                                                         h->d_fin_off, h->lay.n_fin, (T *)Ax, (T *)l,
+                                                         (T *)u);
+  SAA_CUDA(h, cudaGetLastError());
+  return SAA_OK;
+}
+
+}  // namespace
+
+#include "car_host.cuh"
+#include "hopper_host.cuh"
+
+// =============================================================================
+// C ABI
+// =============================================================================
+extern "C" {
+
+int saa_version(void) { return kVersion; }
+
+const char *saa_last_error(const saa_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int saa_create(saa_handle **out, int problem, int method, int variant, int64_t M_local,
+               int64_t M_global, int64_t sample_offset, int S, double alpha, int precision,
+               int device) {
+  if (!out) return fail(nullptr, SAA_ERR_ARG, "out is NULL");
+  *out = nullptr;
+  if (problem < SAA_DRONE || problem > SAA_HOPPER) return fail(nullptr, SAA_ERR_ARG, "unknown problem");
+  if (method != SAA_METHOD_SAA && method != SAA_METHOD_BASELINE) return fail(nullptr, SAA_ERR_ARG, "unknown method");
+  if (precision != 64 && precision != 32) return fail(nullptr, SAA_ERR_ARG, "precision must be 64 or 32");
+  if (M_local <= 0 || M_global < M_local || sample_offset < 0 || sample_offset + M_local > M_global)
+    return fail(nullptr, SAA_ERR_ARG, "need 0 < M_local <= M_global and the local range inside the global one");
+  if (problem != SAA_HOPPER && S != kS)
+    return fail(nullptr, SAA_ERR_ARG, "this build instantiates the kernels for S = 20 (the reference horizon)");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(nullptr, SAA_ERR_NO_DEVICE, "no CUDA device: libsaa_b200 has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(nullptr, SAA_ERR_ARG, "bad device index");
+  if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, SAA_ERR_CUDA, "cudaSetDevice failed");
+  saa_handle *h = new (std::nothrow) saa_handle();
+  if (!h) return fail(nullptr, SAA_ERR_ARG, "out of host memory");
+  h->problem = problem; h->method = method; h->variant = variant; h->S = S;
+  h->precision = precision; h->device = device;
+  h->M_local = M_local; h->M_global = M_global; h->sample_offset = sample_offset; h->alpha = alpha;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->n_sms = prop.multiProcessorCount;
+  if (problem != SAA_HOPPER) {
+    int rc = set_geometry(h, M_global, sample_offset);
+    if (rc) { g_create_error = h->err; delete h; return rc; }
+  }
+  *out = h;
+  return SAA_OK;
+}
+
+int saa_destroy(saa_handle *h) {
+  if (!h) return SAA_OK;
+  cudaSetDevice(h->device);
+  cudaFree(h->d_a); cudaFree(h->d_b); cudaFree(h->d_c); cudaFree(h->d_d);
+  cudaFree(h->d_partials); cudaFree(h->d_sums); cudaFree(h->d_fin_off);
+  delete h;
+  return SAA_OK;
+}
+
+int saa_set_params_drone(saa_handle *h, const saa_drone_params *p) {
+  if (!h || !p) return fail(h, SAA_ERR_ARG, "NULL argument");
+  if (h->problem != SAA_DRONE) return fail(h, SAA_ERR_ARG, "handle is not a drone problem");
+  if (p->n_obs != 3) return fail(h, SAA_ERR_ARG, "kernels are instantiated for n_obs = 3");
+  if (!(p->dt > 0)) return fail(h, SAA_ERR_ARG, "dt must be positive");
+  h->dp = *p; h->params_set = true;
+  return SAA_OK;
+}
+
+int saa_set_samples_drone(saa_handle *h, const double *masses, const double *DWs, const double *obs_Qs,
+                          void *stream) {
+  if (!h || !masses || !DWs || !obs_Qs) return fail(h, SAA_ERR_ARG, "NULL argument");
+  if (h->problem != SAA_DRONE) return fail(h, SAA_ERR_ARG, "handle is not a drone problem");
+  SAA_CUDA(h, cudaSetDevice(h->device));
+  const i64 M = h->M_local;
+  h->Mpad = (M + kTileSamples - 1) / kTileSamples * kTileSamples;
+  const size_t es = esize(h);
+  if (!h->d_a) {
+    SAA_CUDA(h, cudaMalloc(&h->d_a, h->Mpad * es));
+    SAA_CUDA(h, cudaMalloc(&h->d_b, h->Mpad * es * 3 * h->S));
+    SAA_CUDA(h, cudaMalloc(&h->d_c, h->Mpad * es * 6));
+  }
+  const int threads = 128;
+  const int blocks = (int)((h->Mpad + threads - 1) / threads);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (h->precision == 64)
+    drone_pack_kernel<double><<<blocks, threads, 0, st>>>(masses, DWs, obs_Qs, M, h->Mpad, h->S,
+                                                        (double *)h->d_a, (double *)h->d_b, (double *)h->d_c);
+  else
+    drone_pack_kernel<float><<<blocks, threads, 0, st>>>(masses, DWs, obs_Qs, M, h->Mpad, h->S,
+                                                       (float *)h->d_a, (float *)h->d_b, (float *)h->d_c);
+  SAA_CUDA(h, cudaGetLastError());
+  h->samples_set = true;
+  return SAA_OK;
+}
+
+int saa_pattern_sizes(const saa_handle *h, int relaxed_pattern, int64_t *n_rows, int64_t *n_cols,
+                      int64_t *nnz) {
+  if (!h) return fail(h, SAA_ERR_ARG, "NULL handle");
+  if (h->problem == SAA_HOPPER) return fail(h, SAA_ERR_ARG, "hopper has no QP pattern");
+  Layout L; L.build(h->problem, h->method, h->S, h->M_out, relaxed_pattern != 0);
+  if (n_rows) *n_rows = L.n_rows;
+  if (n_cols) *n_cols = L.n_cols;
+  if (nnz) *nnz = L.nnz;
+  return SAA_OK;
+}
+
+int saa_pattern_i32(const saa_handle *h, int relaxed_pattern, int32_t *indptr, int32_t *indices) {
+  if (!h || !indptr || !indices) return fail(h, SAA_ERR_ARG, "NULL argument");
+  if (h->problem == SAA_HOPPER) return fail(h, SAA_ERR_ARG, "hopper has no QP pattern");
+  Layout L; L.build(h->problem, h->method, h->S, h->M_out, relaxed_pattern != 0);
+  if (L.nnz > 2147483647LL || L.n_rows > 2147483647LL)
+    return fail(h, SAA_ERR_ARG, "pattern needs 64-bit indices: use saa_pattern_i64");
+  L.fill<int32_t>(indptr, indices);
+  return SAA_OK;
+}
+
+int saa_pattern_i64(const saa_handle *h, int relaxed_pattern, int64_t *indptr, int64_t *indices) {
+  if (!h || !indptr || !indices) return fail(h, SAA_ERR_ARG, "NULL argument");
+  if (h->problem == SAA_HOPPER) return fail(h, SAA_ERR_ARG, "hopper has no QP pattern");
+  Layout L; L.build(h->problem, h->method, h->S, h->M_out, relaxed_pattern != 0);
+  L.fill<int64_t>(indptr, indices);
+  return SAA_OK;
+}
+
+static int static_args_ok(int problem, int method, int S, int64_t M) {
+  if (problem != SAA_DRONE && problem != SAA_CAR) return fail(nullptr, SAA_ERR_ARG, "pattern: drone or car only");
+  if (method != SAA_METHOD_SAA && method != SAA_METHOD_BASELINE) return fail(nullptr, SAA_ERR_ARG, "unknown method");
+  if (S < 2 || M < 1) return fail(nullptr, SAA_ERR_ARG, "need S >= 2 and M >= 1");
+  return SAA_OK;
+}
+
+int saa_static_pattern_sizes(int problem, int method, int S, int64_t M, int relaxed_pattern,
+                             int64_t *n_rows, int64_t *n_cols, int64_t *nnz) {
+  if (int rc = static_args_ok(problem, method, S, M)) return rc;
+  Layout L; L.build(problem, method, S, M, relaxed_pattern != 0);
+  if (n_rows) *n_rows = L.n_rows;
+  if (n_cols) *n_cols = L.n_cols;
+  if (nnz) *nnz = L.nnz;
+  return SAA_OK;
+}
+
+int saa_static_pattern_i32(int problem, int method, int S, int64_t M, int relaxed_pattern,
+                           int32_t *indptr, int32_t *indices) {
+  if (int rc = static_args_ok(problem, method, S, M)) return rc;
+  if (!indptr || !indices) return fail(nullptr, SAA_ERR_ARG, "NULL argument");
+  Layout L; L.build(problem, method, S, M, relaxed_pattern != 0);
+  if (L.nnz > 2147483647LL || L.n_rows > 2147483647LL)
+    return fail(nullptr, SAA_ERR_ARG, "pattern needs 64-bit indices");
+  L.fill<int32_t>(indptr, indices);
+  return SAA_OK;
+}
+
+int saa_static_pattern_i64(int problem, int method, int S, int64_t M, int relaxed_pattern,
+                           int64_t *indptr, int64_t *indices) {
+  if (int rc = static_args_ok(problem, method, S, M)) return rc;
+  if (!indptr || !indices) return fail(nullptr, SAA_ERR_ARG, "NULL argument");
+  Layout L; L.build(problem, method, S, M, relaxed_pattern != 0);
+  L.fill<int64_t>(indptr, indices);
+  return SAA_OK;
+}
+
+int saa_set_output_geometry(saa_handle *h, int64_t M_out, int64_t first_out) {
+  if (!h) return fail(h, SAA_ERR_ARG, "NULL handle");
+  if (h->problem == SAA_HOPPER) return fail(h, SAA_ERR_ARG, "hopper has no QP geometry");
+  SAA_CUDA(h, cudaSetDevice(h->device));
+  return set_geometry(h, M_out, first_out);
+}
+
+int saa_write_constants(saa_handle *h, int scp_iter, int write_shared, void *Ax, void *l, void *u,
+                        void *stream) {
+  if (!h || !Ax || !l || !u) return fail(h, SAA_ERR_ARG, "NULL argument");
+  if (h->problem == SAA_HOPPER) return fail(h, SAA_ERR_ARG, "hopper has no QP constants");
+  if (!h->params_set) return fail(h, SAA_ERR_STATE, "set params first");
+  SAA_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (h->problem == SAA_CAR && scp_iter < 1)
+    return car_write_constants_relaxed(h, write_shared, Ax, l, u, st);
+  return h->precision == 64 ? launch_constants<double>(h, scp_iter, write_shared, Ax, l, u, st)
+                            : launch_constants<float>(h, scp_iter, write_shared, Ax, l, u, st);
+}
+
+int64_t saa_mean_len(const saa_handle *h) {
+  if (!h) return 0;
+  if (h->problem == SAA_DRONE) return DroneRed<kS>::N;
+  if (h->problem == SAA_CAR) return CarRed<kS>::N;
+  return 0;
+}
+
+int saa_finalize_means(saa_handle *h, const double *mean_sums, void *Ax, void *l, void *u, void *stream) {
+  if (!h || !mean_sums || !Ax || !l || !u) return fail(h, SAA_ERR_ARG, "NULL argument");
+  if (h->problem == SAA_HOPPER) return fail(h, SAA_ERR_ARG, "hopper has no mean rows");
+  SAA_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  return h->precision == 64 ? launch_finalize<double>(h, mean_sums, Ax, l, u, st)
+                            : launch_finalize<float>(h, mean_sums, Ax, l, u, st);
+}
+
+int saa_linearize_assemble(saa_handle *h, const double *us, int scp_iter, void *Ax, void *l, void *u,
+                           void *Z, double *mean_sums, int finalize, void *stream) {
+  if (!h || !us || !Ax || !u || !l) return fail(h, SAA_ERR_ARG, "NULL argument");
+  if (h->problem == SAA_HOPPER) return fail(h, SAA_ERR_ARG, "use saa_hopper_friction for the hopper");
+  if (!h->params_set || !h->samples_set) return fail(h, SAA_ERR_STATE, "set params and samples first");
+  SAA_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  int grid = 0, rc;
+  if (h->problem == SAA_DRONE)
+    rc = h->precision == 64 ? launch_drone_assemble<double>(h, us, scp_iter, Ax, u, Z, &grid, st)
+                            : launch_drone_assemble<float>(h, us, scp_iter, Ax, u, Z, &grid, st);
+  else
+    rc = h->precision == 64 ? launch_car_assemble<double>(h, us, scp_iter, Ax, u, Z, &grid, st)
+                            : launch_car_assemble<float>(h, us, scp_iter, Ax, u, Z, &grid, st);
+  if (rc) return rc;
+  const int n = (int)saa_mean_len(h);
+  double *sums = mean_sums ? mean_sums : h->d_sums;
+  reduce_partials_kernel<double><<<(n + 127) / 128, 128, 0, st>>>(h->d_partials, grid, n, sums);
+  SAA_CUDA(h, cudaGetLastError());
+  if (finalize) return saa_finalize_means(h, sums, Ax, l, u, stream);
+  return SAA_OK;
+}
+
+int saa_rollout(saa_handle *h, const double *us, void *Xs, void *stream) {
+  if (!h || !us || !Xs) return fail(h, SAA_ERR_ARG, "NULL argument");
+  if (h->problem == SAA_HOPPER) return fail(h, SAA_ERR_ARG, "the hopper trajectory is a decision variable");
+  if (!h->params_set || !h->samples_set) return fail(h, SAA_ERR_STATE, "set params and samples first");
+  SAA_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (h->problem == SAA_DRONE)
+    return h->precision == 64 ? launch_drone_rollout<double>(h, us, Xs, nullptr, 0, 0, 0, nullptr, st)
+                              : launch_drone_rollout<float>(h, us, Xs, nullptr, 0, 0, 0, nullptr, st);
+  return h->precision == 64 ? launch_car_rollout<double>(h, us, Xs, nullptr, 0, 0, 0, nullptr, st)
+                            : launch_car_rollout<float>(h, us, Xs, nullptr, 0, 0, 0, nullptr, st);
+}
+
+int saa_cvar_terms(saa_handle *h, const double *us, double t_risk, double sat_tol, void *Z,
+                   double *out3, void *stream) {
+  if (!h || !us || !out3) return fail(h, SAA_ERR_ARG, "NULL argument");
+  if (h->problem == SAA_HOPPER) return fail(h, SAA_ERR_ARG, "use saa_hopper_friction for the hopper");
+  if (!h->params_set || !h->samples_set) return fail(h, SAA_ERR_STATE, "set params and samples first");
+  SAA_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (h->problem == SAA_DRONE) {
+    const double tol = h->dp.osqp_tol;
+    return h->precision == 64 ? launch_drone_rollout<double>(h, us, nullptr, Z, t_risk, sat_tol, tol, out3, st)
+                              : launch_drone_rollout<float>(h, us, nullptr, Z, t_risk, sat_tol, tol, out3, st);
+  }
+  const double tol = h->cp.osqp_tol;
+  return h->precision == 64 ? launch_car_rollout<double>(h, us, nullptr, Z, t_risk, sat_tol, tol, out3, st)
+                            : launch_car_rollout<float>(h, us, nullptr, Z, t_risk, sat_tol, tol, out3, st);
+}
+
+}  // extern "C"

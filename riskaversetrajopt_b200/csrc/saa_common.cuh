@@ -1,0 +1,93 @@
+// Shared helpers for libsaa_b200 (sm_100a).  See include/saa_b200.h for the ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/saa_b200.h"
+
+namespace saa {
+
+typedef long long i64;
+
+constexpr int kTileSamples = 16;   // samples per warp tile: lanes = 16 samples x 2 "roles"
+constexpr int kSMs = 148;          // B200
+
+// ----------------------------------------------------------------------------
+// Layout of the assembled matrix for `M` samples (closed form, no scanning).
+// Row order / column order: include/saa_b200.h header comment.
+// ----------------------------------------------------------------------------
+struct Layout {
+  int problem = 0, method = 0;
+  int S = 0, n_u = 0, n_x = 0, n_fin = 0;
+  int blk = 1;          // constraint groups per step (drone: n_obs = 3, car: 1)
+  int R = 0;            // sample rows per sample = blk * S
+  i64 M = 0;            // samples in the destination matrix
+  bool relaxed_pattern = false;   // car scp_iter == 0: rows >= n_x vanish
+  // rows
+  i64 row_cvar = -1, row_y0 = -1, row_s0 = 0, row_slack = -1, row_ctrl0 = 0, n_rows = 0;
+  // columns
+  int nu = 0;
+  i64 n_cols = 0, nnz = 0;
+  i64 ycol0 = 0, slackcol = 0, tcol = 0;   // element offsets of the first y column, slack, t
+  std::vector<i64> ucol;                   // element offset of each u column (nu + 1)
+
+  // number of final rows hit by u column c, and which
+  int fin_rows(int c, int rows[4]) const;
+  // sample-run length per sample in u column c (0 if the column carries no sample rows)
+  int run_len(int c) const;
+  i64 run_start(int c) const { int r[4]; return ucol[c] + fin_rows(c, r); }
+  i64 ycol_len() const;   // entries per y column
+  void build(int problem_, int method_, int S_, i64 M_, bool relaxed_pattern_);
+  template <typename I> void fill(I *indptr, I *indices) const;
+};
+
+// ----------------------------------------------------------------------------
+// device helpers
+// ----------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T sum16(T v) {   // sum over the 16 lanes that share lane>>4
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v;
+}
+template <typename T>
+__device__ __forceinline__ T sum32(T v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 16);
+  return sum16(v);
+}
+template <typename T>
+__device__ __forceinline__ T max32(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Optimisation barrier: the value is unchanged but the compiler must assume it
+// was modified.  Used to stop common-subexpression hoisting across the fully
+// unrolled sensitivity chains (which would keep ~60 extra doubles live and spill).
+__device__ __forceinline__ void opaque(double &v) { asm volatile("" : "+d"(v)); }
+__device__ __forceinline__ void opaque(float &v) { asm volatile("" : "+f"(v)); }
+__device__ __forceinline__ void opaque(i64 &v) { asm volatile("" : "+l"(v)); }
+
+// streaming (evict-first) store: assembled values are never re-read by this kernel
+template <typename T>
+__device__ __forceinline__ void st_stream(T *p, T v) { __stcs(p, v); }
+
+// Copy a run of n = n_samples * LEN values, staged in shared memory with row
+// stride STRIDE (>= LEN, odd => conflict-free 64-bit STS from 16 lanes), to a
+// contiguous global run.  Consecutive lanes -> consecutive addresses.
+template <typename T, int LEN, int STRIDE>
+__device__ __forceinline__ void copy_run(T *__restrict__ dst, const T *__restrict__ src,
+                                         int n, int lane) {
+#pragma unroll 4
+  for (int e = lane; e < n; e += 32) {
+    const int i = e / LEN;
+    st_stream(dst + e, src[e + i * (STRIDE - LEN)]);
+  }
+}
+
+}  // namespace saa

@@ -1,0 +1,57 @@
+"""Mint the golden vectors under tests/golden/ from Oracle-A (the literal
+autodiff restatement of the reference) at the reference's seeds.
+
+    python tests/golden/make_golden.py
+
+The reference itself cannot run in this image (no jax/osqp/ipyopt), ships no
+stored outputs and has no tests, so these files are minted from the oracle and
+pin it against regressions; what pins the oracle is described in
+oracle/__init__.py.  Inputs are regenerated from the seeds at test time, only
+outputs are stored.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from oracle.oracle_a import DroneOracleA  # noqa: E402
+from riskaversetrajopt_b200.drone import drone_params as dp  # noqa: E402
+from riskaversetrajopt_b200.drone.drone_utils import sample_uncertain_parameters  # noqa: E402
+
+
+def drone():
+    np.random.seed(0)                                   # drone_risk.py:57
+    DWs, masses, obs_Qs = sample_uncertain_parameters('saa', M=dp.M)   # first repeat, :483-484
+    # (1) reference defaults: M = 50, alpha = 0.1, initial guess, scp_iter = 2
+    m = DroneOracleA(dp.S, DWs, masses, obs_Qs, 'saa', 0.1)
+    us = m.initial_guess_us_mat()
+    A, l, u = m.get_constraints_coeffs(us, 2)
+    Xs = m.us_to_state_trajectories(us)
+    sat, Z = m.monte_carlo_constraints(us)
+    np.savez_compressed(os.path.join(HERE, "drone_M50_saa_iter2.npz"), us=us, shape=A.shape,
+                        indptr=A.indptr, indices=A.indices, data=A.data, l=l, u=u,
+                        Xs_first3=Xs[:3], Z=Z)
+    # (2) first 8 samples, perturbed iterate, all branches
+    rs = np.random.RandomState(123)
+    us = m.initial_guess_us_mat() + 0.5 * rs.randn(dp.S, dp.n_u)
+    out = dict(us=us)
+    for method in ('saa', 'baseline'):
+        for variant in ('risk', 'times'):
+            mm = DroneOracleA(dp.S, DWs[:8], masses[:8], obs_Qs[:8], method, 0.05, variant)
+            for it in (0, 2):
+                A, l, u = mm.get_constraints_coeffs(us, it)
+                k = f"{method}_{variant}_{it}"
+                out[k + "_indptr"], out[k + "_indices"] = A.indptr, A.indices
+                out[k + "_data"], out[k + "_l"], out[k + "_u"] = A.data, l, u
+    np.savez_compressed(os.path.join(HERE, "drone_M8_branches.npz"), **out)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["drone", "car", "hopper"]
+    for name in which:
+        if name in globals():
+            globals()[name]()
+            print("minted", name)
