@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsaa_b200.so")
+# SAA_B200_LIB lets kernel experiments load an alternative build of the same ABI
+LIB_PATH = os.environ.get("SAA_B200_LIB") or os.path.join(_HERE, "libsaa_b200.so")
 
 SAA_DRONE, SAA_CAR, SAA_HOPPER = 0, 1, 2
 SAA_METHOD_SAA, SAA_METHOD_BASELINE = 0, 1

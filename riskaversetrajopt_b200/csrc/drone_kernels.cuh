@@ -23,6 +23,23 @@
 #pragma once
 #include "saa_common.cuh"
 
+// ---- tuning switches (defaults = the measured best; see profiles/ and DESIGN.md) ----
+#ifndef SAA_PRELOAD
+#define SAA_PRELOAD 1      // load the tile's noise increments before the rollouts
+#endif
+#ifndef SAA_PREFETCH
+#define SAA_PREFETCH 0     // prefetch.global.L2 of the next tile's input lines
+#endif
+#ifndef SAA_PAIR
+#define SAA_PAIR 0         // process chains (J, S-2-J) together
+#endif
+#ifndef SAA_COPY
+#define SAA_COPY 0         // 0: simple loop, 1: 8-deep batches inline, 2: shared non-inlined body
+#endif
+#ifndef SAA_BPS
+#define SAA_BPS 2          // resident blocks per SM the kernel is compiled for
+#endif
+
 namespace saa {
 
 template <int S> struct DroneRed {
@@ -50,86 +67,152 @@ template <typename T, int S> struct DroneArgs {
   double *partials;         // [gridDim.x][DroneRed<S>::N]
 };
 
-// ---- one sensitivity chain: column (j, axis) --------------------------------
-template <typename T, int S, int J> struct DroneChain {
+// ---- sensitivity chains ----------------------------------------------------------
+// Column (J, axis) of a sample holds rows k = J+2..S for each of the 3 obstacles:
+// LEN = 3 (S-1-J) contiguous values.  Chains are processed in pairs (J, S-2-J) so
+// that every pass has the same amount of work (LEN1 + LEN2 = 3S) and two
+// independent dependency chains per thread (ILP).
+template <int S, int J> struct DroneChain {
   static constexpr int L = S - 1 - J;      // rows k = J+2..S carry an entry
   static constexpr int LEN = 3 * L;        // per-sample run length in the CSC column
-  static constexpr int STRIDE = LEN | 1;   // odd stride: conflict-free staging
+  static constexpr int STRIDE = LEN | 1;   // odd stride: conflict-free 64-bit staging stores
 };
 
+template <typename T, int S> struct DroneChainState {
+  T sp, sv;
+};
+
+// one step k -> k+1 of chain J, staging the three entries of row k+1
 template <typename T, int S, int J>
-__device__ __forceinline__ void drone_chain(const T (&P)[S + 1], const T (&A22)[S],
-                                            const T (&q2)[3], const T (&oca)[3],
-                                            T dt, T a21, T dtm, T *stage_mine,
-                                            T &sp_out, T &sv_out) {
-  using C = DroneChain<T, S, J>;
-  T q2j[3] = {q2[0], q2[1], q2[2]};
-  T ocj[3] = {oca[0], oca[1], oca[2]};
-  // recompute the coefficients per chain: registers over flops
-  opaque(q2j[0]); opaque(q2j[1]); opaque(q2j[2]);
-  opaque(ocj[0]); opaque(ocj[1]); opaque(ocj[2]);
-  T sp = T(0), sv = dtm;                   // d(p,v)_{J+1} / du_J
+__device__ __forceinline__ void drone_chain_step(int k, const T (&P)[S + 1], const T (&A22)[S],
+                                                 const T (&q2)[3], const T (&oc)[3], T dt, T a21,
+                                                 T *mine, DroneChainState<T, S> &c) {
+  using C = DroneChain<S, J>;
+  const T nsp = fma(dt, c.sv, c.sp);
+  const T nsv = fma(A22[k], c.sv, a21 * c.sp);
+  c.sp = nsp; c.sv = nsv;                  // now d(p,v)_{k+1} / du_J
+  const int kk = k - J - 1;
 #pragma unroll
-  for (int k = J + 1; k < S; ++k) {
-    const T nsp = fma(dt, sv, sp);
-    const T nsv = fma(A22[k], sv, a21 * sp);
-    sp = nsp; sv = nsv;                    // now d(p,v)_{k+1} / du_J
-    const int kk = k - J - 1;              // row (k+1) is the kk-th row of this column's run
-#pragma unroll
-    for (int o = 0; o < 3; ++o) {
-      const T coef = q2j[o] * (P[k + 1] - ocj[o]);   // escale * d g[o,k+1] / d p
-      stage_mine[o * C::L + kk] = coef * sp;
-    }
+  for (int o = 0; o < 3; ++o) {
+    const T coef = q2[o] * (P[k + 1] - oc[o]);     // escale * d g[o,k+1] / d p
+    mine[o * C::L + kk] = coef * c.sp;
   }
-  sp_out = sp; sv_out = sv;
 }
 
 template <typename T, int S, int WARPS>
 struct DroneSmem {
-  static constexpr int STAGE = 2 * kTileSamples * (3 * (S - 1));   // elements per warp
+  static constexpr int STAGE = 2 * kTileSamples * (3 * S + 2);   // elements per warp
   T stage[WARPS][STAGE];
   double wacc[WARPS][DroneRed<S>::N];
 };
 
+// Copy n = ns*LEN staged values (row stride LEN + EXTRA) to a contiguous global run.
+template <typename T>
+__device__ __noinline__ void copy_run_rt(T *__restrict__ dst, const T *__restrict__ src, int n,
+                                         int extra, unsigned magic) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll 1
+  for (int e0 = lane; e0 < n; e0 += 256) {
+    T v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int e = min(e0 + u * 32, n - 1);
+      v[u] = src[e + (int)__umulhi((unsigned)e, magic) * extra];
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (e0 + u * 32 < n) st_stream(dst + e0 + u * 32, v[u]);
+  }
+}
+template <typename T, int LEN, int EXTRA>
+__device__ __forceinline__ void copy_run8(T *__restrict__ dst, const T *__restrict__ src, int n,
+                                          int lane) {
+  constexpr unsigned MAGIC = (unsigned)((0x100000000ull + LEN - 1) / LEN);
+#if SAA_COPY == 2
+  copy_run_rt<T>(dst, src, n, EXTRA, MAGIC);
+#elif SAA_COPY == 1
+#pragma unroll 1
+  for (int e0 = lane; e0 < n; e0 += 256) {
+    T v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int e = min(e0 + u * 32, n - 1);
+      const int i = EXTRA ? (int)__umulhi((unsigned)e, MAGIC) : 0;
+      v[u] = src[e + i * EXTRA];
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (e0 + u * 32 < n) st_stream(dst + e0 + u * 32, v[u]);
+  }
+#else
+  copy_run<T, LEN, LEN + EXTRA>(dst, src, n, lane);
+#endif
+}
+
 template <typename T, int S, int J>
-__device__ __forceinline__ void drone_chain_loop(const DroneArgs<T, S> &A, const T (&P)[S + 1],
-                                                 const T (&A22)[S], const T (&q2)[3],
-                                                 const T (&oca)[3], T a21, T dtm, T *stage,
-                                                 double *wacc, int a, int si, int lane, i64 s0,
-                                                 int ns, bool active) {
+__device__ __forceinline__ void drone_chain_pairs(const DroneArgs<T, S> &A, const T (&P)[S + 1],
+                                                  const T (&A22)[S], const T (&q2)[3],
+                                                  const T (&oca)[3], T a21, T dtm, T *stage,
+                                                  double *wacc, int a, int si, int lane, i64 s0,
+                                                  int ns, bool active) {
   using Rd = DroneRed<S>;
-  if constexpr (J == S - 1) {
-    // last control step: no sample rows, only d v_S/du = dt/m in the mean rows
+  constexpr int J2 = SAA_PAIR ? S - 2 - J : J;            // partner chain (J2 >= J)
+  if constexpr (SAA_PAIR ? (J > J2) : (J >= S - 1)) {
+    // all chains with sample rows are done; last control step J = S-1 has none:
+    // only d v_S/du = dt/m enters the mean rows
     const double rv = sum16((double)(active ? dtm : T(0)));
     if (si == 0) wacc[Rd::FIN_V + a * S + (S - 1)] += rv;
   } else {
-    using C = DroneChain<T, S, J>;
-    T sp, sv;
-    T *mine = stage + (a * kTileSamples + si) * C::STRIDE;
-    drone_chain<T, S, J>(P, A22, q2, oca, A.dt, a21, dtm, mine, sp, sv);
-    // sample-mean rows: d p_S / du_J and d v_S / du_J summed over the tile
-    const double rp = sum16((double)(active ? sp : T(0)));
-    const double rv = sum16((double)(active ? sv : T(0)));
-    if (si == 0) {
-      wacc[Rd::FIN_P + a * (S - 1) + J] += rp;
-      wacc[Rd::FIN_V + a * S + J] += rv;
+    using C1 = DroneChain<S, J>;
+    using C2 = DroneChain<S, J2>;
+    constexpr bool PAIR = (J2 != J);
+    // optimisation barriers: keep per-chain coefficient math from being hoisted
+    // (common subexpressions across the unrolled chains would cost ~60 live doubles)
+    T q2j[3] = {q2[0], q2[1], q2[2]}, ocj[3] = {oca[0], oca[1], oca[2]};
+    opaque(q2j[0]); opaque(q2j[1]); opaque(q2j[2]);
+    opaque(ocj[0]); opaque(ocj[1]); opaque(ocj[2]);
+    T *mine1 = stage + (a * kTileSamples + si) * C1::STRIDE;
+    T *mine2 = stage + 2 * kTileSamples * C1::STRIDE + (a * kTileSamples + si) * C2::STRIDE;
+    DroneChainState<T, S> c1{T(0), dtm}, c2{T(0), dtm};   // d(p,v)_{J+1}/du_J = (0, dt/m)
+#pragma unroll
+    for (int k = J + 1; k < S; ++k) {
+      drone_chain_step<T, S, J>(k, P, A22, q2j, ocj, A.dt, a21, mine1, c1);
+      if (PAIR && k >= J2 + 1) drone_chain_step<T, S, J2>(k, P, A22, q2j, ocj, A.dt, a21, mine2, c2);
+    }
+    // sample-mean rows: d p_S/du_J, d v_S/du_J summed over the tile
+    {
+      const double rp = sum16((double)(active ? c1.sp : T(0)));
+      const double rv = sum16((double)(active ? c1.sv : T(0)));
+      if (si == 0) { wacc[Rd::FIN_P + a * (S - 1) + J] += rp; wacc[Rd::FIN_V + a * S + J] += rv; }
+    }
+    if (PAIR) {
+      const double rp = sum16((double)(active ? c2.sp : T(0)));
+      const double rv = sum16((double)(active ? c2.sv : T(0)));
+      if (si == 0) { wacc[Rd::FIN_P + a * (S - 1) + J2] += rp; wacc[Rd::FIN_V + a * S + J2] += rv; }
     }
     __syncwarp();
-    const int n = ns * C::LEN;
-    i64 base = s0 * C::LEN;
-    opaque(base);   // keep the 2(S-1) column bases in the constant bank, not hoisted into registers
-    copy_run<T, C::LEN, C::STRIDE>(A.Ax + (A.col_off[J] + base), stage, n, lane);
-    copy_run<T, C::LEN, C::STRIDE>(A.Ax + (A.col_off[(S - 1) + J] + base),
-                                   stage + kTileSamples * C::STRIDE, n, lane);
+    i64 sbase = s0;
+    opaque(sbase);   // keep the 2(S-1) column bases in the constant bank, not hoisted into registers
+    copy_run8<T, C1::LEN, C1::STRIDE - C1::LEN>(A.Ax + (A.col_off[J] + sbase * C1::LEN), stage,
+                                                ns * C1::LEN, lane);
+    copy_run8<T, C1::LEN, C1::STRIDE - C1::LEN>(A.Ax + (A.col_off[(S - 1) + J] + sbase * C1::LEN),
+                                                stage + kTileSamples * C1::STRIDE, ns * C1::LEN, lane);
+    if (PAIR) {
+      const T *st2 = stage + 2 * kTileSamples * C1::STRIDE;
+      copy_run8<T, C2::LEN, C2::STRIDE - C2::LEN>(A.Ax + (A.col_off[J2] + sbase * C2::LEN), st2,
+                                                  ns * C2::LEN, lane);
+      copy_run8<T, C2::LEN, C2::STRIDE - C2::LEN>(A.Ax + (A.col_off[(S - 1) + J2] + sbase * C2::LEN),
+                                                  st2 + kTileSamples * C2::STRIDE, ns * C2::LEN, lane);
+    }
     __syncwarp();
-    drone_chain_loop<T, S, J + 1>(A, P, A22, q2, oca, a21, dtm, stage, wacc, a, si, lane, s0, ns,
-                                  active);
+    drone_chain_pairs<T, S, J + 1>(A, P, A22, q2, oca, a21, dtm, stage, wacc, a, si, lane, s0, ns,
+                                   active);
   }
 }
 
 // ---- K1: linearize + assemble ------------------------------------------------
 template <typename T, int S, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 2)
+__global__ void __launch_bounds__(WARPS * 32, SAA_BPS)
 drone_assemble_kernel(const __grid_constant__ DroneArgs<T, S> A) {
   using Rd = DroneRed<S>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -142,12 +225,34 @@ drone_assemble_kernel(const __grid_constant__ DroneArgs<T, S> A) {
   __syncwarp();
 
   const i64 ntiles = (A.M + kTileSamples - 1) / kTileSamples;
-  for (i64 tile = (i64)blockIdx.x * WARPS + warp; tile < ntiles; tile += (i64)gridDim.x * WARPS) {
+  const i64 tstride = (i64)gridDim.x * WARPS;
+#pragma unroll 1
+  for (i64 tile = (i64)blockIdx.x * WARPS + warp; tile < ntiles; tile += tstride) {
     const i64 s0 = tile * kTileSamples;
     const int ns = (int)min((i64)kTileSamples, A.M - s0);
     const bool active = si < ns;
     const i64 s = s0 + (active ? si : 0);
-    const T inv_m = T(1) / A.mass[s];
+    // ---- all inputs of the tile in flight at once (one DRAM round trip) ----------
+    const T *dwz_p = A.dw + 2 * A.Mpad + s, *dwa_p = A.dw + a * A.Mpad + s;
+    T dwz[S], dwa[S];
+#pragma unroll
+    for (int k = 0; k < S; ++k) { if (SAA_PRELOAD) dwz[k] = __ldcs(dwz_p + (i64)k * 3 * A.Mpad); }
+#pragma unroll
+    for (int k = 0; k < S; ++k) { if (SAA_PRELOAD) dwa[k] = __ldcs(dwa_p + (i64)k * 3 * A.Mpad); }
+    T q[3];
+#pragma unroll
+    for (int o = 0; o < 3; ++o) q[o] = __ldcs(A.q + (o * 2 + a) * A.Mpad + s);
+    const T mass = __ldcs(A.mass + s);
+    // ... and the next tile's lines on their way into L2 (67 lines of 128 B per tile)
+    if (SAA_PREFETCH && tile + tstride < ntiles) {
+      const i64 sn = s0 + tstride * kTileSamples;
+      for (int r = lane; r < 3 * S + 7; r += 32) {
+        const T *pf = r < 3 * S ? A.dw + (i64)r * A.Mpad + sn
+                    : r < 3 * S + 6 ? A.q + (i64)(r - 3 * S) * A.Mpad + sn : A.mass + sn;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+      }
+    }
+    const T inv_m = T(1) / mass;
     const T dt = A.dt, dtm = dt * inv_m, a21 = -A.kp * dtm;
     const T nz = A.noise_c * inv_m;
     const T c2 = T(2) * A.drag;
@@ -166,7 +271,7 @@ drone_assemble_kernel(const __grid_constant__ DroneArgs<T, S> A) {
         const T ntp = fma(dt, tv, tp);
         const T ntv = fma(a22, tv, fma(a21, tp, dtm * u));
         const T np_ = fma(dt, v, p);
-        v = v + dt * acc + nz * A.dw[(k * 3 + 2) * A.Mpad + s];
+        v = v + dt * acc + nz * (SAA_PRELOAD ? dwz[k] : dwz_p[(i64)k * 3 * A.Mpad]);
         p = np_; tp = ntp; tv = ntv;
       }
       // linearisation offset of the final rows: -(x_S - x_f) + d x_S/du . u  (:271)
@@ -190,10 +295,9 @@ drone_assemble_kernel(const __grid_constant__ DroneArgs<T, S> A) {
 
     // ---------------- own axis (x or y): rollout + constraint values ----------
     T P[S + 1], A22[S];
-    T q[3], q2[3], oca[3];
+    T q2[3], oca[3];
 #pragma unroll
     for (int o = 0; o < 3; ++o) {
-      q[o] = A.q[(o * 2 + a) * A.Mpad + s];
       q2[o] = T(-2) * A.escale * q[o];
       oca[o] = a ? A.oc[o][1] : A.oc[o][0];
     }
@@ -211,7 +315,7 @@ drone_assemble_kernel(const __grid_constant__ DroneArgs<T, S> A) {
         const T ntp = fma(dt, tv, tp);
         const T ntv = fma(a22, tv, fma(a21, tp, dtm * u));
         const T np_ = fma(dt, v, p);
-        v = v + dt * acc + nz * A.dw[(k * 3 + a) * A.Mpad + s];
+        v = v + dt * acc + nz * (SAA_PRELOAD ? dwa[k] : dwa_p[(i64)k * 3 * A.Mpad]);
         p = np_; tp = ntp; tv = ntv;
         P[k + 1] = p;
 #pragma unroll
@@ -233,13 +337,13 @@ drone_assemble_kernel(const __grid_constant__ DroneArgs<T, S> A) {
       if (A.Z != nullptr && a == 0 && active) A.Z[s] = zmax - A.ztol;
       __syncwarp();
       if (A.ub != nullptr)
-        copy_run<T, 3 * S, 3 * S + 1>(A.ub + A.ub_off + s0 * (3 * S), stage, ns * 3 * S, lane);
+        copy_run8<T, 3 * S, 1>(A.ub + A.ub_off + s0 * (3 * S), stage, ns * 3 * S, lane);
       __syncwarp();
     }
 
-    // ---------------- sensitivity chains, one CSC column pair per control step -
-    drone_chain_loop<T, S, 0>(A, P, A22, q2, oca, a21, dtm, stage, wacc, a, si, lane, s0, ns,
-                              active);
+    // ---------------- sensitivity chains, two CSC column pairs per pass ---------
+    drone_chain_pairs<T, S, 0>(A, P, A22, q2, oca, a21, dtm, stage, wacc, a, si, lane, s0, ns,
+                               active);
   }
 
   // ---------------- per-block partial sums (fixed order => deterministic) -----
@@ -254,14 +358,16 @@ drone_assemble_kernel(const __grid_constant__ DroneArgs<T, S> A) {
 
 // ---- finalize: sum block partials in block order, divide, scatter ------------
 // sums_out (optional): the plain sums, for the multi-GPU all-reduce.
+// one warp per slot: lanes stride over the blocks, then a fixed-order butterfly
 template <typename T>
 __global__ void reduce_partials_kernel(const double *__restrict__ partials, int nblocks, int n,
                                        double *__restrict__ sums_out) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (r >= n) return;
   double acc = 0.0;
-  for (int b = 0; b < nblocks; ++b) acc += partials[(i64)b * n + r];
-  sums_out[r] = acc;
+  for (int b = lane; b < nblocks; b += 32) acc += partials[(i64)b * n + r];
+  acc = sum32(acc);
+  if (lane == 0) sums_out[r] = acc;
 }
 
 template <typename T>

@@ -17,8 +17,11 @@ namespace {
 
 constexpr int kVersion = 100;
 constexpr int kS = 20;            // horizon the kernels are instantiated for (reference: S = 20)
-constexpr int kWarps = 6;         // warps per block of the assemble kernels (2 blocks / SM)
-constexpr int kBlocksPerSM = 2;
+#ifndef SAA_WARPS
+#define SAA_WARPS 6
+#endif
+constexpr int kWarps = SAA_WARPS;    // warps per block of the assemble kernels
+constexpr int kBlocksPerSM = SAA_BPS; // resident blocks per SM (persistent grid = SMs x this)
 
 thread_local std::string g_create_error;
 
@@ -524,7 +527,7 @@ int saa_linearize_assemble(saa_handle *h, const double *us, int scp_iter, void *
   if (rc) return rc;
   const int n = (int)saa_mean_len(h);
   double *sums = mean_sums ? mean_sums : h->d_sums;
-  reduce_partials_kernel<double><<<(n + 127) / 128, 128, 0, st>>>(h->d_partials, grid, n, sums);
+  reduce_partials_kernel<double><<<(n + 3) / 4, 128, 0, st>>>(h->d_partials, grid, n, sums);
   SAA_CUDA(h, cudaGetLastError());
   if (finalize) return saa_finalize_means(h, sums, Ax, l, u, stream);
   return SAA_OK;

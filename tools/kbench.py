@@ -1,0 +1,45 @@
+"""Kernel micro-benchmark for build variants: python tools/kbench.py lib1.so lib2.so ...
+Each library is timed in its own subprocess (drone assemble, M = 10^6, CUDA events)."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CHILD = r'''
+import sys, os, numpy as np, torch
+sys.path.insert(0, %r)
+import bench
+from riskaversetrajopt_b200 import _lib
+from riskaversetrajopt_b200.device_path import DevicePath
+from riskaversetrajopt_b200.drone import drone_params as dp
+M = int(os.environ.get("KB_M", "1000000"))
+dev = torch.device("cuda", 0)
+DWs, masses, obs_Qs = bench.synthetic_drone_samples(M, 0, dev)
+path = DevicePath(_lib.SAA_DRONE, 'saa', 20, 0.1, M, device=0)
+path.set_params_drone(dp, dp.OSQP_TOL); path.set_samples_drone(masses, DWs, obs_Qs)
+torch.cuda.synchronize(); del DWs, masses, obs_Qs; path._keep = []
+us = bench.bench_us()
+for _ in range(3): path.assemble(us, 2)
+torch.cuda.synchronize()
+ts = []
+for _ in range(10):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); path.assemble(us, 2, finalize=False); b.record(); torch.cuda.synchronize()
+    ts.append(a.elapsed_time(b))
+# checksum so that variants can be compared for equality
+buf = path.buffers()
+print("RESULT", float(np.median(ts)), float(min(ts)), float(buf['Ax'][:1140 * M].sum().item()), float(buf['u'].sum().item()))
+''' % ROOT
+
+for lib in sys.argv[1:]:
+    env = dict(os.environ, SAA_B200_LIB=os.path.abspath(lib))
+    out = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True)
+    line = [l for l in out.stdout.splitlines() if l.startswith("RESULT")]
+    if line:
+        _, med, mn, cs1, cs2 = line[0].split()
+        gbs = 10144 * int(os.environ.get("KB_M", "1000000")) / (float(med) * 1e-3) / 1e9
+        print(f"{os.path.basename(lib):28s} median {float(med):7.3f} ms  min {float(mn):7.3f} ms  {gbs:7.1f} GB/s  "
+              f"frac {gbs / 6555.8:.3f}  checksum {cs1} {cs2}", flush=True)
+    else:
+        print(os.path.basename(lib), "FAILED", out.stderr[-800:], flush=True)
