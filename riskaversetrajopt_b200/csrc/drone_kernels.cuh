@@ -34,7 +34,7 @@
 #define SAA_PAIR 0         // process chains (J, S-2-J) together
 #endif
 #ifndef SAA_COPY
-#define SAA_COPY 0         // 0: simple loop, 1: 8-deep batches inline, 2: shared non-inlined body
+#define SAA_COPY 0         // 0: simple loop, 1: 8-deep batches inline, 2: shared non-inlined body, 3: TMA bulk stores
 #endif
 #ifndef SAA_BPS
 #define SAA_BPS 2          // resident blocks per SM the kernel is compiled for
@@ -60,7 +60,9 @@ template <typename T, int S> struct DroneArgs {
   T ubscale, ubpad;         // upper bound = ubscale * (-g + grad g . u) - ubpad
   T ztol;                   // Z_i = max g - ztol
   T *Ax;
-  i64 col_off[2 * (S - 1)]; // [a*(S-1)+j]: offset in Ax of local sample 0's sub-run of column (j,a)
+  // Sub-run of local sample 0 in u column (j, a): Ax + CA(j,a) + M_out*CB(j,a) + first_out*LEN(j)
+  // with compile-time CA, CB (DroneChain); the host checks them against Layout::run_start.
+  i64 M_out, first_out;
   T *ub;                    // base of the upper-bound vector (nullptr: skip)
   i64 ub_off;               // row of local sample 0's first sample row
   T *Z;                     // per-sample max constraint (nullptr: skip)
@@ -76,6 +78,11 @@ template <int S, int J> struct DroneChain {
   static constexpr int L = S - 1 - J;      // rows k = J+2..S carry an entry
   static constexpr int LEN = 3 * L;        // per-sample run length in the CSC column
   static constexpr int STRIDE = LEN | 1;   // odd stride: conflict-free 64-bit staging stores
+  // CSC position of sample 0's run of column c = 3J + a in a matrix with M samples is
+  // CAa + M * CBa: every earlier control step holds 6 final-row + 3 control-row
+  // entries and 2 columns of 3(S-1-j') values per sample (layout.cuh, Layout::build)
+  static constexpr i64 CA0 = 9 * J + 2, CA1 = CA0 + 3;
+  static constexpr i64 CB0 = 6 * J * (S - 1) - 3 * J * (J - 1), CB1 = CB0 + 3 * (S - 1 - J);
 };
 
 template <typename T, int S> struct DroneChainState {
@@ -101,7 +108,7 @@ __device__ __forceinline__ void drone_chain_step(int k, const T (&P)[S + 1], con
 
 template <typename T, int S, int WARPS>
 struct DroneSmem {
-  static constexpr int STAGE = 2 * kTileSamples * (3 * S + 2);   // elements per warp
+  static constexpr int STAGE = 2 * kTileSamples * (3 * S + 2) + 8;   // elements per warp (>= every Stager<T,LEN>::SIZE)
   T stage[WARPS][STAGE];
   double wacc[WARPS][DroneRed<S>::N];
 };
@@ -171,8 +178,21 @@ __device__ __forceinline__ void drone_chain_pairs(const DroneArgs<T, S> &A, cons
     T q2j[3] = {q2[0], q2[1], q2[2]}, ocj[3] = {oca[0], oca[1], oca[2]};
     opaque(q2j[0]); opaque(q2j[1]); opaque(q2j[2]);
     opaque(ocj[0]); opaque(ocj[1]); opaque(ocj[2]);
+#if SAA_COPY == 3
+    static_assert(!SAA_PAIR, "TMA copy-out is implemented for single chains");
+    using St = Stager<T, C1::LEN>;
+    static_assert(St::SIZE <= DroneSmem<T, S, 1>::STAGE, "staging buffer too small");
+    i64 sbase = s0 + A.first_out, mout = A.M_out;
+    opaque(sbase); opaque(mout);   // recompute the column bases per chain (2 IMADs) instead of keeping 2(S-1) of them live
+    const i64 g0 = (a ? C1::CA1 + mout * C1::CB1 : C1::CA0 + mout * C1::CB0) + sbase * C1::LEN;
+    T *mine1 = St::mine(stage, a, si, g0);
+    T *mine2 = mine1;
+    bulk_wait_read();              // the previous column pair has left the staging buffer
+    __syncwarp();
+#else
     T *mine1 = stage + (a * kTileSamples + si) * C1::STRIDE;
     T *mine2 = stage + 2 * kTileSamples * C1::STRIDE + (a * kTileSamples + si) * C2::STRIDE;
+#endif
     DroneChainState<T, S> c1{T(0), dtm}, c2{T(0), dtm};   // d(p,v)_{J+1}/du_J = (0, dt/m)
 #pragma unroll
     for (int k = J + 1; k < S; ++k) {
@@ -190,21 +210,27 @@ __device__ __forceinline__ void drone_chain_pairs(const DroneArgs<T, S> &A, cons
       const double rv = sum16((double)(active ? c2.sv : T(0)));
       if (si == 0) { wacc[Rd::FIN_P + a * (S - 1) + J2] += rp; wacc[Rd::FIN_V + a * S + J2] += rv; }
     }
+#if SAA_COPY == 3
+    fence_async_smem();
     __syncwarp();
-    i64 sbase = s0;
-    opaque(sbase);   // keep the 2(S-1) column bases in the constant bank, not hoisted into registers
-    copy_run8<T, C1::LEN, C1::STRIDE - C1::LEN>(A.Ax + (A.col_off[J] + sbase * C1::LEN), stage,
-                                                ns * C1::LEN, lane);
-    copy_run8<T, C1::LEN, C1::STRIDE - C1::LEN>(A.Ax + (A.col_off[(S - 1) + J] + sbase * C1::LEN),
+    St::flush(A.Ax, stage, a, si, g0, ns);
+#else
+    __syncwarp();
+    i64 sbase = s0 + A.first_out, mout = A.M_out;
+    opaque(sbase); opaque(mout);   // recompute the column bases per chain (2 IMADs) instead of keeping 2(S-1) of them live
+    copy_run8<T, C1::LEN, C1::STRIDE - C1::LEN>(A.Ax + (C1::CA0 + mout * C1::CB0 + sbase * C1::LEN),
+                                                stage, ns * C1::LEN, lane);
+    copy_run8<T, C1::LEN, C1::STRIDE - C1::LEN>(A.Ax + (C1::CA1 + mout * C1::CB1 + sbase * C1::LEN),
                                                 stage + kTileSamples * C1::STRIDE, ns * C1::LEN, lane);
     if (PAIR) {
       const T *st2 = stage + 2 * kTileSamples * C1::STRIDE;
-      copy_run8<T, C2::LEN, C2::STRIDE - C2::LEN>(A.Ax + (A.col_off[J2] + sbase * C2::LEN), st2,
-                                                  ns * C2::LEN, lane);
-      copy_run8<T, C2::LEN, C2::STRIDE - C2::LEN>(A.Ax + (A.col_off[(S - 1) + J2] + sbase * C2::LEN),
+      copy_run8<T, C2::LEN, C2::STRIDE - C2::LEN>(A.Ax + (C2::CA0 + mout * C2::CB0 + sbase * C2::LEN),
+                                                  st2, ns * C2::LEN, lane);
+      copy_run8<T, C2::LEN, C2::STRIDE - C2::LEN>(A.Ax + (C2::CA1 + mout * C2::CB1 + sbase * C2::LEN),
                                                   st2 + kTileSamples * C2::STRIDE, ns * C2::LEN, lane);
     }
     __syncwarp();
+#endif
     drone_chain_pairs<T, S, J + 1>(A, P, A22, q2, oca, a21, dtm, stage, wacc, a, si, lane, s0, ns,
                                    active);
   }
@@ -305,6 +331,15 @@ drone_assemble_kernel(const __grid_constant__ DroneArgs<T, S> A) {
       T p = a ? A.x0[1] : A.x0[0], v = a ? A.x0[4] : A.x0[3], tp = T(0), tv = T(0);
       T zmax = -INFINITY;
       P[0] = p;
+#if SAA_COPY == 3
+      using StU = Stager<T, 3 * S>;
+      const i64 gu = A.ub_off + s0 * (3 * S);
+      T *ubrow = StU::mine(stage, 0, si, gu);
+      bulk_wait_read();            // last column pair of the previous tile
+      __syncwarp();
+#else
+      T *ubrow = stage + si * (3 * S + 1);
+#endif
 #pragma unroll
       for (int k = 0; k < S; ++k) {
         const T absv = fabs(v);
@@ -327,7 +362,7 @@ drone_assemble_kernel(const __grid_constant__ DroneArgs<T, S> A) {
           const T esum = e + __shfl_xor_sync(0xffffffffu, e, 16);
           zmax = fmax(zmax, T(1) - wsum);
           if (a == (k & 1))                               // the two lanes of a sample share the stores
-            stage[si * (3 * S + 1) + o * S + k] = fma(esum - T(1), A.ubscale, -A.ubpad);
+            ubrow[o * S + k] = fma(esum - T(1), A.ubscale, -A.ubpad);
         }
       }
       const T valp = -(p - (a ? A.xf[1] : A.xf[0])) + tp, valv = -(v - (a ? A.xf[4] : A.xf[3])) + tv;
@@ -335,10 +370,16 @@ drone_assemble_kernel(const __grid_constant__ DroneArgs<T, S> A) {
       const double rv = sum16((double)(active ? valv : T(0)));
       if (si == 0) { wacc[Rd::VAL + a] += rp; wacc[Rd::VAL + 3 + a] += rv; }
       if (A.Z != nullptr && a == 0 && active) A.Z[s] = zmax - A.ztol;
+#if SAA_COPY == 3
+      fence_async_smem();
+      __syncwarp();
+      if (A.ub != nullptr && a == 0) StU::flush(A.ub, stage, 0, si, gu, ns);
+#else
       __syncwarp();
       if (A.ub != nullptr)
         copy_run8<T, 3 * S, 1>(A.ub + A.ub_off + s0 * (3 * S), stage, ns * 3 * S, lane);
       __syncwarp();
+#endif
     }
 
     // ---------------- sensitivity chains, two CSC column pairs per pass ---------
@@ -346,6 +387,9 @@ drone_assemble_kernel(const __grid_constant__ DroneArgs<T, S> A) {
                                active);
   }
 
+#if SAA_COPY == 3
+  bulk_wait_all();
+#endif
   // ---------------- per-block partial sums (fixed order => deterministic) -----
   __syncthreads();
   for (int r = threadIdx.x; r < Rd::N; r += WARPS * 32) {

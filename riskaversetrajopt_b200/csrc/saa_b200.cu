@@ -240,6 +240,11 @@ int grid_for(const saa_handle *h, i64 ntiles, int warps, int blocks_per_sm) {
   return (int)std::max<i64>(1, std::min<i64>(want, (i64)h->n_sms * blocks_per_sm));
 }
 
+// same formula as DroneChain<S,J>::CA/CB (drone_kernels.cuh)
+i64 drone_col_start(int j, int a, int S, i64 M) {
+  return (9 * j + 3 * a + 2) + M * (i64)(6 * j * (S - 1) - 3 * j * (j - 1) + 3 * a * (S - 1 - j));
+}
+
 template <typename T>
 int launch_drone_assemble(saa_handle *h, const double *us, int scp_iter, void *Ax, void *u, void *Z,
                           int *grid_out, cudaStream_t st) {
@@ -257,11 +262,12 @@ int launch_drone_assemble(saa_handle *h, const double *us, int scp_iter, void *A
   A.ubscale = (T)mult; A.ubpad = (T)pad; A.ztol = (T)0;
   A.Ax = (T *)Ax;
   const Layout &L = h->lay;
+  A.M_out = h->M_out; A.first_out = h->first_out;
+  // the kernel derives the column positions in closed form; they must agree with the layout
   for (int a = 0; a < 2; ++a)
-    for (int j = 0; j < kS - 1; ++j) {
-      const int c = j * 3 + a;
-      A.col_off[a * (kS - 1) + j] = L.run_start(c) + h->first_out * L.run_len(c);
-    }
+    for (int j = 0; j < kS - 1; ++j)
+      if (L.run_start(j * 3 + a) != drone_col_start(j, a, kS, h->M_out))
+        return fail(h, SAA_ERR_STATE, "internal: closed-form column offsets disagree with the layout");
   A.ub = relaxed ? nullptr : (T *)u;          // relaxed: bounds are the constant +-bound
   A.ub_off = L.row_s0 + h->first_out * L.R;
   A.Z = (T *)Z;

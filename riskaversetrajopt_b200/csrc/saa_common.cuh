@@ -90,4 +90,80 @@ __device__ __forceinline__ void copy_run(T *__restrict__ dst, const T *__restric
   }
 }
 
+
+// ----------------------------------------------------------------------------
+// TMA bulk stores (cp.async.bulk, shared::cta -> global): the copy engine moves a
+// staged run to global memory asynchronously; no LDS/STG/index instructions.
+// Both addresses must be 16-byte aligned and the size a multiple of 16 bytes.
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+               "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all of this thread's bulk groups have finished READING shared memory (buffer reusable)
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// make this thread's generic-proxy shared-memory writes visible to the async proxy (TMA)
+__device__ __forceinline__ void fence_async_smem() {
+#ifndef SAA_TMA_NOFENCE
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+}
+
+// Staging geometry of one CSC column pair (x and y column of a control step):
+// 16 sample rows of LEN values per column.
+//  * dense (row stride LEN): one bulk store per column run.  Conflict-free 64-bit
+//    stores for odd LEN, 2-way for LEN = 2 (mod 4).
+//  * row-wise (LEN = 0 mod 4 would be 4..16-way conflicted when dense): padded row
+//    stride LEN + VEC, every lane bulk-stores its own row.
+// A run that starts at global element g0 is staged at offset (g0 mod VEC) so that
+// 16-byte aligned global addresses map to 16-byte aligned shared addresses; the
+// (< VEC) head / tail elements go out as plain stores.
+template <typename T, int LEN> struct Stager {
+  static constexpr int VEC = 16 / (int)sizeof(T);
+#ifdef SAA_TMA_DENSE_ONLY
+  static constexpr bool ROWWISE = false;
+#else
+  static constexpr bool ROWWISE = (LEN % (2 * VEC) == 0);
+#endif
+  static constexpr int RSTRIDE = LEN + VEC;
+  static constexpr int YBASE = ((kTileSamples * LEN + VEC - 1) / VEC + 1) * VEC;
+  static constexpr int SIZE = ROWWISE ? 2 * kTileSamples * RSTRIDE : 2 * YBASE;
+
+  __device__ __forceinline__ static T *mine(T *stage, int a, int si, i64 g0) {
+    const int off = (int)(g0 & (VEC - 1));
+    return ROWWISE ? stage + (a * kTileSamples + si) * RSTRIDE + off
+                   : stage + a * YBASE + off + si * LEN;
+  }
+  // call after fence_async_smem() + __syncwarp(); g0 = global element index (in `base`) of the
+  // tile's run of column a; ns = valid sample rows
+  __device__ __forceinline__ static void flush(T *base, T *stage, int a, int si, i64 g0, int ns) {
+    const int off = (int)(g0 & (VEC - 1));
+    const int head = (VEC - off) & (VEC - 1);
+    if (ROWWISE) {
+      if (si < ns) {
+        T *row = stage + (a * kTileSamples + si) * RSTRIDE + off;
+        T *dst = base + g0 + (i64)si * LEN;
+        constexpr int dummy = 0; (void)dummy;
+        const int bulk = ((LEN - head) / VEC) * VEC, tail = LEN - head - bulk;
+        bulk_store(dst + head, row + head, bulk * (unsigned)sizeof(T));
+        for (int e = 0; e < head; ++e) st_stream(dst + e, row[e]);
+        for (int e = 0; e < tail; ++e) st_stream(dst + head + bulk + e, row[head + bulk + e]);
+      }
+    } else if (si == 0) {
+      const int n = ns * LEN;
+      T *run = stage + a * YBASE + off;
+      T *dst = base + g0;
+      const int h = head < n ? head : n;
+      const int bulk = ((n - h) / VEC) * VEC, tail = n - h - bulk;
+      if (bulk > 0) bulk_store(dst + h, run + h, bulk * (unsigned)sizeof(T));
+      for (int e = 0; e < h; ++e) st_stream(dst + e, run[e]);
+      for (int e = 0; e < tail; ++e) st_stream(dst + h + bulk + e, run[h + bulk + e]);
+    }
+    bulk_commit();
+  }
+};
+
 }  // namespace saa
