@@ -168,7 +168,7 @@ int64_t saa_mean_len(const saa_handle *h);
 /* after an all-reduce(sum) of mean_sums over ranks: mean = sums / M_global ->
  * final rows of Ax, l[0..n_fin), u[0..n_fin).
  * replaces: jnp.mean(...) drone/drone_risk.py:294-300, car/driving.py:311-317 */
-int saa_finalize_means(saa_handle *h, const double *mean_sums_dev,
+int saa_finalize_means(saa_handle *h, const double *mean_sums_dev, int scp_iter,
                        void *Ax_dev, void *l_dev, void *u_dev, void *stream);
 
 /* Rollout only: Xs_dev (M_local, S+1, n_x) row-major.

@@ -171,3 +171,137 @@ class DroneOracleB:
             Z = np.maximum(Z, np.max(1.0 - np.sum(Qd[:, None, :] * d * d, axis=-1), axis=1))
         Z = Z - dp.OSQP_TOL
         return Z <= 1e-6, Z
+
+
+# =============================================================================
+# Car + pedestrian
+# =============================================================================
+class CarOracleB:
+    """Analytic restatement of car/driving.py:145-421.  Forward sensitivities with
+    the full 8x8 step Jacobian  A_k = I + dt db/dx  (ego block
+    d(px',py')/d(v,phi) = dt [[cos, -v sin], [sin, v cos]]; pedestrian block
+    dF/dp_ego = G = -w_r (I - n n^T)/|d| = -dF/dp_ped, dF_{0,1}/dx7 = -w_s) and
+    B = dt [e_2, e_3]:  X_{k+1} = A_k X_k + B_k with X_k = d x_k / d u (8 x 40).
+    Deliberately the generic dense recursion, not the reduced one the CUDA
+    kernel uses, so that the two check each other."""
+
+    def __init__(self, states_init, omegas_speed, omegas_repulsive, DWs, method='saa', alpha=0.05):
+        self.method, self.alpha = method, alpha
+        self.x0 = np.asarray(states_init, dtype=np.float64)
+        self.w_s = np.asarray(omegas_speed, dtype=np.float64)
+        self.w_r = np.asarray(omegas_repulsive, dtype=np.float64)
+        self.DWs = np.asarray(DWs, dtype=np.float64)
+        self.M, self.S, self.dt, self.beta = self.w_s.shape[0], cp.S, cp.dt, 3e-2
+
+    def rollout(self, us_mat, with_jac=False):
+        S, dt, M = self.S, self.dt, self.M
+        us = np.asarray(us_mat, dtype=np.float64)
+        Xs = np.empty((M, S + 1, 8))
+        Xs[:, 0] = self.x0
+        J = np.zeros((M, S + 1, 8, 2 * S)) if with_jac else None
+        for t in range(S):
+            x = Xs[:, t]
+            d = x[:, 0:2] - x[:, 4:6]
+            n = np.linalg.norm(d, axis=1)
+            F = -self.w_r[:, None] * d / n[:, None] + (self.w_s * (cp.speed_ped_des - x[:, 7]))[:, None]
+            b = np.stack([x[:, 2] * np.cos(x[:, 3]), x[:, 2] * np.sin(x[:, 3]),
+                          np.full(M, us[t, 0]), np.full(M, us[t, 1]),
+                          x[:, 6], x[:, 7], F[:, 0], F[:, 1]], axis=1)
+            noise = np.zeros((M, 8))
+            noise[:, 6:] = np.sqrt(dt) * self.beta * self.DWs[:, t, 6:]
+            Xs[:, t + 1] = x + dt * b + noise
+            if with_jac:
+                A = np.zeros((M, 8, 8))
+                A[:, 0, 2], A[:, 0, 3] = np.cos(x[:, 3]), -x[:, 2] * np.sin(x[:, 3])
+                A[:, 1, 2], A[:, 1, 3] = np.sin(x[:, 3]), x[:, 2] * np.cos(x[:, 3])
+                A[:, 4, 6] = 1.0
+                A[:, 5, 7] = 1.0
+                nh = d / n[:, None]
+                G = -(self.w_r / n)[:, None, None] * (np.eye(2)[None] - nh[:, :, None] * nh[:, None, :])
+                A[:, 6:8, 0:2] = G
+                A[:, 6:8, 4:6] = -G
+                A[:, 6, 7] += -self.w_s
+                A[:, 7, 7] += -self.w_s
+                A = np.eye(8)[None] + dt * A
+                J[:, t + 1] = A @ J[:, t]
+                J[:, t + 1, 2, 2 * t] += dt
+                J[:, t + 1, 3, 2 * t + 1] += dt
+        return (Xs, J) if with_jac else Xs
+
+    def per_sample(self, us_mat):
+        S = self.S
+        us = np.asarray(us_mat, dtype=np.float64)
+        u_vec = us.reshape(2 * S)
+        Xs, J = self.rollout(us, with_jac=True)
+        goal = np.concatenate([cp.position_ego_goal, cp.velocity_ego_goal])
+        final_du = J[:, S, :4, :]
+        val_final = -(Xs[:, S, :4] - goal) + final_du @ u_vec
+        d = Xs[:, 1:, 0:2] - Xs[:, 1:, 4:6]
+        n = np.linalg.norm(d, axis=2)
+        g = -(n - float(cp.min_separation_distance))
+        nh = d / n[:, :, None]
+        g_du = -(nh[:, :, 0, None] * (J[:, 1:, 0] - J[:, 1:, 4]) + nh[:, :, 1, None] * (J[:, 1:, 1] - J[:, 1:, 5]))
+        g_up = -g + g_du @ u_vec
+        return final_du, val_final, val_final.copy(), g_du, g_up, g
+
+    def get_constraints_coeffs(self, us_mat, scp_iter):
+        S, M = self.S, self.M
+        nu = 2 * S
+        final_du, final_low, final_up, g_du, g_up, _ = self.per_sample(us_mat)
+        fdu = final_du.mean(axis=0)
+        rows, cols, vals = [], [], []
+
+        def add(r, c, v):
+            r, c, v = np.broadcast_arrays(np.asarray(r), np.asarray(c), np.asarray(v, dtype=np.float64))
+            rows.append(r.ravel()); cols.append(c.ravel()); vals.append(v.ravel())
+
+        j = np.arange(S - 1)
+        for cc in range(2):
+            add(0, j * 2 + cc, fdu[0, j * 2 + cc])
+            add(1, j * 2 + cc, fdu[1, j * 2 + cc])
+        j = np.arange(S)
+        add(2, j * 2, fdu[2, j * 2])
+        add(3, j * 2 + 1, fdu[3, j * 2 + 1])
+        i = np.arange(M)
+        if self.method == 'baseline':
+            nrow = 4 + M * S
+            low = -np.inf * np.ones(M * S)
+            up = g_up.reshape(M * S).copy()
+            r0 = 4
+        else:
+            nrow = 4 + 1 + M + M * S + 1
+            low = -np.inf * np.ones(1 + M + M * S + 1)
+            up = np.concatenate([[0.0], np.zeros(M), g_up.reshape(M * S), [0.0]])
+            r0 = 4 + 1 + M
+            add(4, nu + M + 1, M * self.alpha)
+            add(4, nu + np.arange(M + 1), 1.0)
+            add(5 + i, nu + i, -1.0)
+            add(5 + i, nu + M, -1.0)
+            rr = r0 + (i[:, None] * S + np.arange(S)[None, :])
+            add(rr, nu + i[:, None], -1.0)
+            add(rr, nu + M + 1, -1.0)
+            add(nrow - 1, nu + M, -1.0)
+        for k in range(2, S + 1):
+            for cc in range(2):
+                j = np.arange(k - 1)
+                add(r0 + i[:, None] * S + (k - 1), (j * 2 + cc)[None, :], g_du[:, k - 1, :][:, j * 2 + cc])
+        ls = np.hstack([final_low.mean(axis=0), low])
+        us_ = np.hstack([final_up.mean(axis=0), up])
+        rows, cols, vals = map(np.concatenate, (rows, cols, vals))
+        if scp_iter < 1:
+            keep = rows < cp.n_x                # rows >= n_x vanish (multiplied by exactly 0)
+            rows, cols, vals = rows[keep], cols[keep], vals[keep]
+            with np.errstate(invalid='ignore'):
+                ls[cp.n_x:] *= 0
+                us_[cp.n_x:] *= 0
+        c = np.arange(nu)
+        rows = np.concatenate([rows, nrow + c]); cols = np.concatenate([cols, c])
+        vals = np.concatenate([vals, np.ones(nu)])
+        A = sp.coo_matrix((vals, (rows, cols)), shape=(nrow + nu, nu + M + 2)).tocsc()
+        A.sort_indices()
+        return (A, np.hstack([ls, -cp.u_max * np.ones(nu)]), np.hstack([us_, cp.u_max * np.ones(nu)]))
+
+    def monte_carlo_constraints(self, us_mat):
+        _, _, _, _, _, g = self.per_sample(us_mat)
+        Z = g.max(axis=1) - cp.OSQP_TOL
+        return Z <= 1e-6, Z

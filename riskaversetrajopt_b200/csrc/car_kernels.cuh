@@ -17,14 +17,19 @@
 //   rho_{k+1} = rho_k + T_c(k) - dt w_k
 //   w_{k+1}   = w_k + dt (G_k rho_k - w_s w_k.y (1,1)^T),   G_k = -w_r (I - n n^T)/|d_k|, n = d_k/|d_k|
 //   d g_k / d u_{j,c} = -n_k . rho_k                         (non-zero for j <= k-2)
-// All 19 chains of a control advance together in one pass over k (forward mode),
+// All S-1 chains of a control advance together in one pass over k (forward mode),
 // so G_k and n_k are computed once per step.  Lane = (sample, control); a warp owns
 // 16 samples and stages the tile's 16 x 380 entries in shared memory in CSC order
-// [control][j][sample][k], then streams the 38 column sub-runs out coalesced.
+// [control][j][sample][k], then streams the 2(S-1) column sub-runs out coalesced.
 #pragma once
 #include "saa_common.cuh"
 
 namespace saa {
+
+__device__ __forceinline__ double rsqrt_t(double x) { return rsqrt(x); }
+__device__ __forceinline__ float rsqrt_t(float x) { return rsqrtf(x); }
+__device__ __forceinline__ void sincos_t(double x, double *s, double *c) { sincos(x, s, c); }
+__device__ __forceinline__ void sincos_t(float x, float *s, float *c) { sincosf(x, s, c); }
 
 template <int S> struct CarRed {
   static constexpr int PX = 0;                    // + c*(S-1) + j    (c<2, j<S-1)
@@ -35,6 +40,25 @@ template <int S> struct CarRed {
   static constexpr int N = VAL + 4;
 };
 
+// CSC position of sample 0's run of u column 2J + c in a matrix with M samples:
+// CAc + M * CBc.  Every earlier control step holds 2 x (3 final-row + 1 control-row)
+// entries and 2 columns of (S-1-j') values per sample (layout.cuh, Layout::build).
+template <int S, int J> struct CarCol {
+  static constexpr int L = S - 1 - J;
+  static constexpr int STRIDE = L | 1;
+  static constexpr i64 CA0 = 8 * J + 3, CA1 = CA0 + 4;
+  static constexpr i64 CB0 = 2 * J * (S - 1) - J * (J - 1), CB1 = CB0 + L;
+  // staging offset (elements) of column (c, J): columns ordered [c][j], 16 rows each
+  static constexpr int prefix() { int s = 0; for (int j = 0; j < J; ++j) s += kTileSamples * ((S - 1 - j) | 1); return s; }
+  static constexpr int PRE = prefix();
+};
+template <int S> struct CarStage {
+  static constexpr int per_control() { int s = 0; for (int j = 0; j < S - 1; ++j) s += kTileSamples * ((S - 1 - j) | 1); return s; }
+  static constexpr int PER_C = per_control();
+  static constexpr int UB = 2 * PER_C;                 // upper-bound rows: 16 x (S|1)
+  static constexpr int SIZE = UB + kTileSamples * (S | 1);
+};
+
 template <typename T, int S> struct CarArgs {
   const T *x0;       // packed [f*Mpad + s], f = 0..3: pedestrian (qx, qy, wx, wy) initial
   const T *om;       // packed [f*Mpad + s], f = 0: omega_speed, 1: omega_repulsive
@@ -42,34 +66,323 @@ template <typename T, int S> struct CarArgs {
   i64 M, Mpad;
   T us[S * 2];
   T ego0[4];         // ego initial (px, py, v, phi) (same for every sample)
+  T goal[4];
   T dt, noise_c, v_des, d_min;
-  T escale;          // scale applied to the Jacobian entries (1, or 0 -> not used)
   T ztol;
-  T *Ax;
-  i64 col_off[2 * (S - 1)];   // [c*(S-1)+j]
+  T *Ax; i64 M_out, first_out;
   T *ub; i64 ub_off;
   T *Z;
+  double *sums;      // CarRed<S>::N doubles: M * (sample-independent final-row values)
 };
 
-// Ego trajectory, shared by the whole block: E[k] = (px,py,v,phi)_k, TT[c][k] = T_c(k)
+// Ego trajectory, shared by the whole block
 template <typename T, int S> struct CarEgo {
-  T e[S + 1][4];
-  T tt[2][S][2];
-  T ucum[2][S + 1];   // ucum[c][k] = sum_{j<k} u_{j,c}
+  T p[S + 1][2];      // ego position at step k
+  T tt[2][S][2];      // T_c(k)
+  T ucum[2][S + 1];   // sum_{j<k} u_{j,c}
+  T fin[4];           // ego state at step S
 };
 
+// executed by one thread; O(S) work, identical for all samples (car/driving.py:167-172)
 template <typename T, int S>
-__device__ __forceinline__ void car_ego_rollout(const T *us, const T *ego0, T dt, CarEgo<T, S> &E) {
-  // executed by one thread; O(S) work
+__device__ void car_ego_rollout(const T *us, const T *ego0, T dt, CarEgo<T, S> &E) {
   T px = ego0[0], py = ego0[1], v = ego0[2], phi = ego0[3];
   T u0 = T(0), u1 = T(0);
-  E.ucum[0][0] = T(0); E.ucum[1][0] = T(0);
   for (int k = 0; k < S; ++k) {
-    E.e[k][0] = px; E.e[k][1] = py; E.e[k][2] = v; E.e[k][3] = phi;
-    T s, c;
-    sincos((double)phi, (double *)nullptr, (double *)nullptr);  // placeholder removed below
-    (void)s; (void)c;
+    E.p[k][0] = px; E.p[k][1] = py;
+    E.ucum[0][k] = u0; E.ucum[1][k] = u1;
+    T sn, cs;
+    sincos_t(phi, &sn, &cs);
+    const T dt2 = dt * dt;
+    E.tt[0][k][0] = dt2 * cs;      E.tt[0][k][1] = dt2 * sn;
+    E.tt[1][k][0] = -dt2 * v * sn; E.tt[1][k][1] = dt2 * v * cs;
+    px = px + dt * (v * cs);
+    py = py + dt * (v * sn);
+    v = v + dt * us[2 * k];
+    phi = phi + dt * us[2 * k + 1];
+    u0 += us[2 * k]; u1 += us[2 * k + 1];
   }
+  E.p[S][0] = px; E.p[S][1] = py;
+  E.ucum[0][S] = u0; E.ucum[1][S] = u1;
+  E.fin[0] = px; E.fin[1] = py; E.fin[2] = v; E.fin[3] = phi;
+}
+
+// sample-independent final rows (car/driving.py:217-221, :271, :311-313):
+// sums[r] = M * value so that the generic "sum / M_global" finalize applies across ranks
+template <typename T, int S>
+__device__ void car_final_rows(const CarArgs<T, S> &A, const CarEgo<T, S> &E, int tid, int nthreads) {
+  using Rd = CarRed<S>;
+  const double Md = (double)A.M;
+  for (int r = tid; r < Rd::N; r += nthreads) {
+    double val = 0.0;
+    if (r < Rd::V) {                       // d p_S / d u_{j,c} = sum_{m=j+1}^{S-1} T_c(m)
+      const int comp = r >= Rd::PY, q = r - (comp ? Rd::PY : Rd::PX), c = q / (S - 1), j = q % (S - 1);
+      for (int m = j + 1; m < S; ++m) val += (double)E.tt[c][m][comp];
+    } else if (r < Rd::VAL) {              // d v_S / d u_{j,0} = d phi_S / d u_{j,1} = dt
+      val = (double)A.dt;
+    } else {                               // linearisation offset -(ego_S - goal) + J u
+      const int row = r - Rd::VAL;
+      double ju = 0.0;
+      if (row < 2) {
+        for (int c = 0; c < 2; ++c)
+          for (int m = 0; m < S; ++m) ju += (double)E.tt[c][m][row] * (double)E.ucum[c][m];
+      } else {
+        ju = (double)A.dt * (double)E.ucum[row - 2][S];
+      }
+      val = -((double)E.fin[row] - (double)A.goal[row]) + ju;
+    }
+    A.sums[r] = Md * val;
+  }
+}
+
+template <typename T, int S, int WARPS> struct CarSmem {
+  CarEgo<T, S> ego;
+  T stage[WARPS][CarStage<S>::SIZE];
+};
+
+// per-chain sensitivity state
+template <typename T> struct CarChain { T rx, ry, wx, wy; };
+
+// staging offsets of column j inside a control's block (folds to a constant after unrolling)
+template <int S> __device__ __forceinline__ constexpr int car_stride(int j) { return (S - 1 - j) | 1; }
+template <int S> __device__ __forceinline__ constexpr int car_pre(int j) {
+  int s = 0;
+  for (int jj = 0; jj < j; ++jj) s += kTileSamples * car_stride<S>(jj);
+  return s;
+}
+
+template <typename T, int S, int J>
+__device__ __forceinline__ void car_copy_cols(const CarArgs<T, S> &A, const T *stage, i64 sbase, int ns,
+                                              int lane) {
+  if constexpr (J < S - 1) {
+    using C = CarCol<S, J>;
+    i64 sb = sbase, mout = A.M_out;
+    opaque(sb); opaque(mout);   // 2 IMADs per column instead of 2(S-1) live 64-bit bases
+    copy_run<T, C::L, C::STRIDE>(A.Ax + (C::CA0 + mout * C::CB0 + sb * C::L), stage + C::PRE, ns * C::L, lane);
+    copy_run<T, C::L, C::STRIDE>(A.Ax + (C::CA1 + mout * C::CB1 + sb * C::L),
+                                 stage + CarStage<S>::PER_C + C::PRE, ns * C::L, lane);
+    car_copy_cols<T, S, J + 1>(A, stage, sbase, ns, lane);
+  }
+}
+
+// ---- K2: linearize + assemble ---------------------------------------------------
+template <typename T, int S, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+car_assemble_kernel(const __grid_constant__ CarArgs<T, S> A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  auto &sm = *reinterpret_cast<CarSmem<T, S, WARPS> *>(smem_raw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = lane >> 4, si = lane & 15;
+  if (threadIdx.x == 0) car_ego_rollout<T, S>(A.us, A.ego0, A.dt, sm.ego);
+  __syncthreads();
+  if (blockIdx.x == 0 && A.sums != nullptr) car_final_rows<T, S>(A, sm.ego, threadIdx.x, WARPS * 32);
+  if (A.Ax == nullptr) return;              // relaxed iteration: only the final rows are needed
+  const CarEgo<T, S> &E = sm.ego;
+  T *stage = sm.stage[warp];
+  T *cstage = stage + c * CarStage<S>::PER_C;
+  T *ubrow = stage + CarStage<S>::UB + si * (S | 1);
+  const T dt = A.dt;
+
+  const i64 ntiles = (A.M + kTileSamples - 1) / kTileSamples;
+#pragma unroll 1
+  for (i64 tile = (i64)blockIdx.x * WARPS + warp; tile < ntiles; tile += (i64)gridDim.x * WARPS) {
+    const i64 s0 = tile * kTileSamples;
+    const int ns = (int)min((i64)kTileSamples, A.M - s0);
+    const bool active = si < ns;
+    const i64 s = s0 + (active ? si : 0);
+    T dwx[S], dwy[S];
+#pragma unroll
+    for (int k = 0; k < S; ++k) {
+      dwx[k] = __ldcs(A.dw + (i64)(2 * k) * A.Mpad + s);
+      dwy[k] = __ldcs(A.dw + (i64)(2 * k + 1) * A.Mpad + s);
+    }
+    T qx = __ldcs(A.x0 + s), qy = __ldcs(A.x0 + A.Mpad + s);
+    T wx = __ldcs(A.x0 + 2 * A.Mpad + s), wy = __ldcs(A.x0 + 3 * A.Mpad + s);
+    const T w_s = __ldcs(A.om + s), w_r = __ldcs(A.om + A.Mpad + s);
+    const T wsdt = w_s * dt;
+
+    CarChain<T> ch[S - 1];
+    CarChain<T> cu{T(0), T(0), T(0), T(0)};   // tangent along u itself (for grad g . u)
+    T zmax = -INFINITY;
+
+    static_for<0, S + 1>([&](auto kc) {
+      constexpr int k = decltype(kc)::value;
+      // geometry at state k (car/driving.py:150-154, :227-231)
+      const T dx = E.p[k][0] - qx, dy = E.p[k][1] - qy;
+      const T n2 = fma(dx, dx, dy * dy);
+      const T inv_n = rsqrt_t(n2);
+      const T nrm = n2 * inv_n;
+      const T nhx = dx * inv_n, nhy = dy * inv_n;
+      if constexpr (k >= 1) {
+        // row k of the sample: d g_k / d u_{j,c} = -n_k . rho_k^{(j,c)}, live for j <= k-2
+        static_for<0, (k >= 2 ? k - 1 : 0)>([&](auto jc) {
+          constexpr int j = decltype(jc)::value;
+          cstage[CarCol<S, j>::PRE + si * CarCol<S, j>::STRIDE + (k - j - 2)] =
+              -fma(nhx, ch[j].rx, nhy * ch[j].ry);
+        });
+        // upper bound -g_k + grad g_k . u (:278), grad g . u summed over both controls
+        T gu = -fma(nhx, cu.rx, nhy * cu.ry);
+        gu += __shfl_xor_sync(0xffffffffu, gu, 16);
+        const T g = A.d_min - nrm;
+        zmax = fmax(zmax, g);
+        if (c == (k & 1)) ubrow[k - 1] = gu - g;
+      }
+      if constexpr (k < S) {
+        // one Euler-Maruyama step and its linearisation
+        const T om_n = dt * w_r * inv_n;
+        const T g11 = -om_n * fma(-nhx, nhx, T(1)), g12 = om_n * nhx * nhy,
+                g22 = -om_n * fma(-nhy, nhy, T(1));             // dt * dF/dp_ego
+        const T ttx = E.tt[c][k][0], tty = E.tt[c][k][1];
+        static_for<0, (k >= 2 ? k - 1 : 0)>([&](auto jc) {
+          constexpr int j = decltype(jc)::value;
+          const T sy = wsdt * ch[j].wy;
+          const T nwx = fma(g11, ch[j].rx, fma(g12, ch[j].ry, ch[j].wx - sy));
+          const T nwy = fma(g12, ch[j].rx, fma(g22, ch[j].ry, ch[j].wy - sy));
+          ch[j].rx = fma(-dt, ch[j].wx, ch[j].rx + ttx);
+          ch[j].ry = fma(-dt, ch[j].wy, ch[j].ry + tty);
+          ch[j].wx = nwx; ch[j].wy = nwy;
+        });
+        // chain j = k-1 is born at this step: rho_{k+1} = T_c(k), w_{k+1} = 0
+        if constexpr (k >= 1) { ch[k - 1].rx = ttx; ch[k - 1].ry = tty; ch[k - 1].wx = T(0); ch[k - 1].wy = T(0); }
+        {
+          const T uc = E.ucum[c][k];
+          const T sy = wsdt * cu.wy;
+          const T nwx = fma(g11, cu.rx, fma(g12, cu.ry, cu.wx - sy));
+          const T nwy = fma(g12, cu.rx, fma(g22, cu.ry, cu.wy - sy));
+          cu.rx = fma(-dt, cu.wx, fma(uc, ttx, cu.rx));
+          cu.ry = fma(-dt, cu.wy, fma(uc, tty, cu.ry));
+          cu.wx = nwx; cu.wy = nwy;
+        }
+        const T sp = w_s * (A.v_des - wy);
+        const T fx = fma(-w_r, nhx, sp), fy = fma(-w_r, nhy, sp);
+        const T nqx = fma(dt, wx, qx), nqy = fma(dt, wy, qy);
+        wx = wx + dt * fx + A.noise_c * dwx[k];
+        wy = wy + dt * fy + A.noise_c * dwy[k];
+        qx = nqx; qy = nqy;
+      }
+    });
+    if (A.Z != nullptr && c == 0 && active) A.Z[s] = zmax - A.ztol;
+    __syncwarp();
+    if (A.ub != nullptr) copy_run<T, S, (S | 1)>(A.ub + A.ub_off + s0 * S, stage + CarStage<S>::UB, ns * S, lane);
+    car_copy_cols<T, S, 0>(A, stage, s0 + A.first_out, ns, lane);
+    __syncwarp();
+  }
+}
+
+// ---- K4 / K5: rollout only ----------------------------------------------------------
+template <typename T, int S> struct CarRollArgs {
+  const T *x0, *om, *dw;
+  i64 M, Mpad;
+  T us[S * 2];
+  T ego0[4];
+  T dt, noise_c, v_des, d_min;
+  T *Xs;            // (M, S+1, 8) or nullptr
+  T *Z;             // (M) or nullptr
+  T ztol, t_risk, sat_tol;
+  double *partials; // [gridDim.x][3] or nullptr
+};
+
+template <typename T, int S, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+car_rollout_kernel(const __grid_constant__ CarRollArgs<T, S> A) {
+  constexpr int ROW = (S + 1) * 8, STRIDE = ROW | 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ T ego[S + 1][4];
+  __shared__ double red[WARPS][3];
+  T *stage = reinterpret_cast<T *>(smem_raw) + (threadIdx.x >> 5) * 32 * STRIDE;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    T px = A.ego0[0], py = A.ego0[1], v = A.ego0[2], phi = A.ego0[3];
+    for (int k = 0; k <= S; ++k) {
+      ego[k][0] = px; ego[k][1] = py; ego[k][2] = v; ego[k][3] = phi;
+      if (k == S) break;
+      T sn, cs;
+      sincos_t(phi, &sn, &cs);
+      px = px + A.dt * (v * cs); py = py + A.dt * (v * sn);
+      v = v + A.dt * A.us[2 * k]; phi = phi + A.dt * A.us[2 * k + 1];
+    }
+  }
+  __syncthreads();
+  double acc_excess = 0.0, acc_sat = 0.0, acc_max = -INFINITY;
+  const i64 ntiles = (A.M + 31) / 32;
+  for (i64 tile = (i64)blockIdx.x * WARPS + warp; tile < ntiles; tile += (i64)gridDim.x * WARPS) {
+    const i64 s0 = tile * 32;
+    const int ns = (int)min((i64)32, A.M - s0);
+    const bool active = lane < ns;
+    const i64 s = s0 + (active ? lane : 0);
+    T qx = A.x0[s], qy = A.x0[A.Mpad + s], wx = A.x0[2 * A.Mpad + s], wy = A.x0[3 * A.Mpad + s];
+    const T w_s = A.om[s], w_r = A.om[A.Mpad + s];
+    T zmax = -INFINITY;
+    T *mine = stage + lane * STRIDE;
+#pragma unroll 4
+    for (int k = 0; k <= S; ++k) {
+      if (A.Xs != nullptr) {
+#pragma unroll
+        for (int f = 0; f < 4; ++f) mine[k * 8 + f] = ego[k][f];
+        mine[k * 8 + 4] = qx; mine[k * 8 + 5] = qy; mine[k * 8 + 6] = wx; mine[k * 8 + 7] = wy;
+      }
+      const T dx = ego[k][0] - qx, dy = ego[k][1] - qy;
+      const T n2 = fma(dx, dx, dy * dy);
+      const T inv_n = rsqrt_t(n2);
+      if (k >= 1) zmax = fmax(zmax, A.d_min - n2 * inv_n);
+      if (k < S) {
+        const T sp = w_s * (A.v_des - wy);
+        const T fx = fma(-w_r, dx * inv_n, sp), fy = fma(-w_r, dy * inv_n, sp);
+        const T nqx = fma(A.dt, wx, qx), nqy = fma(A.dt, wy, qy);
+        wx = wx + A.dt * fx + A.noise_c * A.dw[(i64)(2 * k) * A.Mpad + s];
+        wy = wy + A.dt * fy + A.noise_c * A.dw[(i64)(2 * k + 1) * A.Mpad + s];
+        qx = nqx; qy = nqy;
+      }
+    }
+    const T Zi = zmax - A.ztol;
+    if (A.Z != nullptr && active) A.Z[s] = Zi;
+    if (active) {
+      acc_excess += (double)fmax(Zi - A.t_risk, T(0));
+      acc_sat += (Zi <= A.sat_tol) ? 1.0 : 0.0;
+      acc_max = fmax(acc_max, (double)Zi);
+    }
+    if (A.Xs != nullptr) {
+      __syncwarp();
+      copy_run<T, ROW, STRIDE>(A.Xs + s0 * ROW, stage, ns * ROW, lane);
+      __syncwarp();
+    }
+  }
+  if (A.partials != nullptr) {
+    acc_excess = sum32(acc_excess); acc_sat = sum32(acc_sat); acc_max = max32(acc_max);
+    if (lane == 0) { red[warp][0] = acc_excess; red[warp][1] = acc_sat; red[warp][2] = acc_max; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double e = 0.0, cc = 0.0, m = -INFINITY;
+      for (int w = 0; w < WARPS; ++w) { e += red[w][0]; cc += red[w][1]; m = fmax(m, red[w][2]); }
+      A.partials[(i64)blockIdx.x * 3 + 0] = e;
+      A.partials[(i64)blockIdx.x * 3 + 1] = cc;
+      A.partials[(i64)blockIdx.x * 3 + 2] = m;
+    }
+  }
+}
+
+// ---- repack the reference-layout sample set (car/driving.py:95-120) ----------------
+template <typename T>
+__global__ void car_pack_kernel(const double *__restrict__ states_init, const double *__restrict__ w_s,
+                                const double *__restrict__ w_r, const double *__restrict__ DWs, i64 M,
+                                i64 Mpad, int S, T *x0, T *om, T *dw) {
+  const i64 s = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= Mpad) return;
+  const i64 src = s < M ? s : M - 1;
+  for (int f = 0; f < 4; ++f) x0[f * Mpad + s] = (T)states_init[src * 8 + 4 + f];
+  om[s] = (T)w_s[src];
+  om[Mpad + s] = (T)w_r[src];
+  for (int k = 0; k < S; ++k)
+    for (int f = 0; f < 2; ++f) dw[(i64)(2 * k + f) * Mpad + s] = (T)DWs[(src * S + k) * 8 + 6 + f];
+}
+
+// Ego initial state must be the same for every sample (the reference only perturbs the
+// pedestrian part, car/driving.py:104-110); checked on the device at set_samples time.
+__global__ void car_check_ego_kernel(const double *__restrict__ states_init, i64 M, int *flag) {
+  const i64 s = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= M) return;
+  for (int f = 0; f < 4; ++f)
+    if (states_init[s * 8 + f] != states_init[f]) *flag = 1;
 }
 
 }  // namespace saa

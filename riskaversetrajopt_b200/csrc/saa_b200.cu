@@ -35,6 +35,7 @@ struct saa_handle {
   bool params_set = false, samples_set = false;
   saa_drone_params dp{};
   saa_car_params cp{};
+  double car_ego0[4] = {0, 0, 0, 0};   // ego initial state (identical for all samples)
   // packed samples (device, library-owned)
   i64 Mpad = 0;
   void *d_a = nullptr, *d_b = nullptr, *d_c = nullptr, *d_d = nullptr;
@@ -44,7 +45,7 @@ struct saa_handle {
   int n_sms = kSMs;
   double *d_partials = nullptr; i64 partials_len = 0;
   double *d_sums = nullptr;
-  i64 *d_fin_off = nullptr;
+  i64 *d_fin_off = nullptr;          // [0..255]: normal pattern, [256..511]: car relaxed pattern
   Layout lay;                 // destination geometry (M_out)
   mutable std::string err;
 };
@@ -92,9 +93,7 @@ int ensure_scratch(saa_handle *h, i64 partial_doubles) {
 
 // offsets (in the destination Ax) of the sample-mean entries, in the order of
 // the kernels' reduction slots
-int upload_fin_offsets(saa_handle *h) {
-  std::vector<i64> off;
-  const Layout &L = h->lay;
+int fin_offsets_for(saa_handle *h, const Layout &L, std::vector<i64> &off) {
   const int S = h->S;
   int rows[4];
   auto pos = [&](int c, int row) -> i64 {
@@ -102,19 +101,34 @@ int upload_fin_offsets(saa_handle *h) {
     for (int r = 0; r < n; ++r) if (rows[r] == row) return L.ucol[c] + r;
     return -1;
   };
+  off.clear();
   if (h->problem == SAA_DRONE) {
     for (int a = 0; a < 3; ++a) for (int j = 0; j < S - 1; ++j) off.push_back(pos(j * 3 + a, a));
     for (int a = 0; a < 3; ++a) for (int j = 0; j < S; ++j) off.push_back(pos(j * 3 + a, 3 + a));
   } else {
-    // car slots: CarRed: PX (c<2, j<S-1), PY (c<2, j<S-1), V (j<S), PHI (j<S)
+    // car slots (CarRed): PX (c<2, j<S-1), PY (c<2, j<S-1), V (j<S), PHI (j<S)
     for (int c = 0; c < 2; ++c) for (int j = 0; j < S - 1; ++j) off.push_back(pos(j * 2 + c, 0));
     for (int c = 0; c < 2; ++c) for (int j = 0; j < S - 1; ++j) off.push_back(pos(j * 2 + c, 1));
     for (int j = 0; j < S; ++j) off.push_back(pos(j * 2 + 0, 2));
     for (int j = 0; j < S; ++j) off.push_back(pos(j * 2 + 1, 3));
   }
   for (i64 o : off) if (o < 0) return fail(h, SAA_ERR_STATE, "internal: final-row offset");
-  if (!h->d_fin_off) SAA_CUDA(h, cudaMalloc(&h->d_fin_off, 256 * sizeof(i64)));
-  SAA_CUDA(h, cudaMemcpy(h->d_fin_off, off.data(), off.size() * sizeof(i64), cudaMemcpyHostToDevice));
+  return SAA_OK;
+}
+
+int upload_fin_offsets(saa_handle *h) {
+  std::vector<i64> off, all(512, 0);
+  int rc = fin_offsets_for(h, h->lay, off);
+  if (rc) return rc;
+  std::copy(off.begin(), off.end(), all.begin());
+  if (h->problem == SAA_CAR) {
+    Layout Lr; Lr.build(h->problem, h->method, h->S, h->M_out, true);
+    rc = fin_offsets_for(h, Lr, off);
+    if (rc) return rc;
+    std::copy(off.begin(), off.end(), all.begin() + 256);
+  }
+  if (!h->d_fin_off) SAA_CUDA(h, cudaMalloc(&h->d_fin_off, 512 * sizeof(i64)));
+  SAA_CUDA(h, cudaMemcpy(h->d_fin_off, all.data(), all.size() * sizeof(i64), cudaMemcpyHostToDevice));
   return SAA_OK;
 }
 
@@ -247,7 +261,7 @@ i64 drone_col_start(int j, int a, int S, i64 M) {
 
 template <typename T>
 int launch_drone_assemble(saa_handle *h, const double *us, int scp_iter, void *Ax, void *u, void *Z,
-                          int *grid_out, cudaStream_t st) {
+                          double *sums, cudaStream_t st) {
   using Args = DroneArgs<T, kS>;
   using Smem = DroneSmem<T, kS, kWarps>;
   Args A{};
@@ -280,7 +294,9 @@ int launch_drone_assemble(saa_handle *h, const double *us, int scp_iter, void *A
   SAA_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
   kern<<<grid, kWarps * 32, sizeof(Smem), st>>>(A);
   SAA_CUDA(h, cudaGetLastError());
-  *grid_out = grid;
+  const int n = DroneRed<kS>::N;
+  reduce_partials_kernel<double><<<(n + 3) / 4, 128, 0, st>>>(h->d_partials, grid, n, sums);
+  SAA_CUDA(h, cudaGetLastError());
   return SAA_OK;
 }
 
@@ -313,11 +329,13 @@ int launch_drone_rollout(saa_handle *h, const double *us, void *Xs, void *Z, dou
 }
 
 template <typename T>
-int launch_finalize(saa_handle *h, const double *sums, void *Ax, void *l, void *u, cudaStream_t st) {
+int launch_finalize(saa_handle *h, const double *sums, int relaxed_pattern, void *Ax, void *l, void *u,
+                    cudaStream_t st) {
   const int n_entries = (int)saa_mean_len(h) - h->lay.n_fin;
   const int n = n_entries + h->lay.n_fin;
+  const i64 *fin_off = h->d_fin_off + ((relaxed_pattern && h->problem == SAA_CAR) ? 256 : 0);
   scatter_means_kernel<T><<<(n + 127) / 128, 128, 0, st>>>(sums, 1.0 / (double)h->M_global, n_entries,
-                                                         h->d_fin_off, h->lay.n_fin, (T *)Ax, (T *)l,
+                                                         fin_off, h->lay.n_fin, (T *)Ax, (T *)l,
                                                          (T *)u);
   SAA_CUDA(h, cudaGetLastError());
   return SAA_OK;
@@ -507,13 +525,15 @@ int64_t saa_mean_len(const saa_handle *h) {
   return 0;
 }
 
-int saa_finalize_means(saa_handle *h, const double *mean_sums, void *Ax, void *l, void *u, void *stream) {
+int saa_finalize_means(saa_handle *h, const double *mean_sums, int scp_iter, void *Ax, void *l, void *u,
+                       void *stream) {
   if (!h || !mean_sums || !Ax || !l || !u) return fail(h, SAA_ERR_ARG, "NULL argument");
   if (h->problem == SAA_HOPPER) return fail(h, SAA_ERR_ARG, "hopper has no mean rows");
   SAA_CUDA(h, cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
-  return h->precision == 64 ? launch_finalize<double>(h, mean_sums, Ax, l, u, st)
-                            : launch_finalize<float>(h, mean_sums, Ax, l, u, st);
+  const int relaxed_pattern = h->problem == SAA_CAR && scp_iter < 1;
+  return h->precision == 64 ? launch_finalize<double>(h, mean_sums, relaxed_pattern, Ax, l, u, st)
+                            : launch_finalize<float>(h, mean_sums, relaxed_pattern, Ax, l, u, st);
 }
 
 int saa_linearize_assemble(saa_handle *h, const double *us, int scp_iter, void *Ax, void *l, void *u,
@@ -523,19 +543,17 @@ int saa_linearize_assemble(saa_handle *h, const double *us, int scp_iter, void *
   if (!h->params_set || !h->samples_set) return fail(h, SAA_ERR_STATE, "set params and samples first");
   SAA_CUDA(h, cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
-  int grid = 0, rc;
-  if (h->problem == SAA_DRONE)
-    rc = h->precision == 64 ? launch_drone_assemble<double>(h, us, scp_iter, Ax, u, Z, &grid, st)
-                            : launch_drone_assemble<float>(h, us, scp_iter, Ax, u, Z, &grid, st);
-  else
-    rc = h->precision == 64 ? launch_car_assemble<double>(h, us, scp_iter, Ax, u, Z, &grid, st)
-                            : launch_car_assemble<float>(h, us, scp_iter, Ax, u, Z, &grid, st);
+  int rc = ensure_scratch(h, 1);
   if (rc) return rc;
-  const int n = (int)saa_mean_len(h);
   double *sums = mean_sums ? mean_sums : h->d_sums;
-  reduce_partials_kernel<double><<<(n + 3) / 4, 128, 0, st>>>(h->d_partials, grid, n, sums);
-  SAA_CUDA(h, cudaGetLastError());
-  if (finalize) return saa_finalize_means(h, sums, Ax, l, u, stream);
+  if (h->problem == SAA_DRONE)
+    rc = h->precision == 64 ? launch_drone_assemble<double>(h, us, scp_iter, Ax, u, Z, sums, st)
+                            : launch_drone_assemble<float>(h, us, scp_iter, Ax, u, Z, sums, st);
+  else
+    rc = h->precision == 64 ? launch_car_assemble<double>(h, us, scp_iter, Ax, u, Z, sums, st)
+                            : launch_car_assemble<float>(h, us, scp_iter, Ax, u, Z, sums, st);
+  if (rc) return rc;
+  if (finalize) return saa_finalize_means(h, sums, scp_iter, Ax, l, u, stream);
   return SAA_OK;
 }
 

@@ -216,10 +216,11 @@ class DevicePath:
                                          int(finalize), self._stream()), self._h)
         return b
 
-    def finalize_means(self, b):
+    def finalize_means(self, b, scp_iter=2):
+        """After an all-reduce(sum) of ``mean_sums`` over the ranks."""
         ptr = lambda t: t.data_ptr() if torch.is_tensor(t) else int(t)
-        check(lib.saa_finalize_means(self._h, self.mean_sums.data_ptr(), ptr(b['Ax']), ptr(b['l']),
-                                     ptr(b['u']), self._stream()), self._h)
+        check(lib.saa_finalize_means(self._h, self.mean_sums.data_ptr(), int(scp_iter), ptr(b['Ax']),
+                                     ptr(b['l']), ptr(b['u']), self._stream()), self._h)
 
     def _pinned_like(self, name, t):
         p = self._pinned.get(name)

@@ -49,6 +49,24 @@ def drone():
     np.savez_compressed(os.path.join(HERE, "drone_M8_branches.npz"), **out)
 
 
+def car():
+    from oracle.oracle_a import CarOracleA, car_sample_parameters
+    np.random.seed(0)                                   # car/driving.py:61
+    samples = car_sample_parameters(50, 'saa')          # first Model(M, 'saa', alpha) of :472
+    m = CarOracleA(*samples, 'saa', 0.05)
+    us0 = m.initial_guess_us_mat()
+    us1 = us0 + 0.4 * np.random.RandomState(7).randn(20, 2)
+    out = dict(us0=us0, us1=us1)
+    for name, us, it in (("iter0", us0, 0), ("iter1", us1, 1), ("iter2", us1, 2)):
+        A, l, u = m.get_constraints_coeffs(us, it)
+        out[name + "_shape"] = np.array(A.shape)
+        out[name + "_indptr"], out[name + "_indices"], out[name + "_data"] = A.indptr, A.indices, A.data
+        out[name + "_l"], out[name + "_u"] = l, u
+    out["Xs_first3"] = m.us_to_state_trajectories(us1)[:3]
+    out["Z"] = m.monte_carlo_constraints(us1)[1]
+    np.savez_compressed(os.path.join(HERE, "car_M50_saa.npz"), **out)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["drone", "car", "hopper"]
     for name in which:

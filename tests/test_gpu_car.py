@@ -1,0 +1,156 @@
+"""Parity of the CUDA path (through the C ABI) with the oracles -- car + pedestrian."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+RTOL64, RTOL32 = 1e-9, 1e-4
+
+
+def _seed0(M=50, method='saa'):
+    from riskaversetrajopt_b200.car.driving import sample_uncertain_parameters
+    state = np.random.get_state()
+    np.random.seed(0)
+    out = sample_uncertain_parameters(M, method)
+    np.random.set_state(state)
+    return out
+
+
+def _check(A, l, u, Ar, lr, ur, rtol=RTOL64):
+    assert A.shape == Ar.shape
+    assert A.indptr.dtype == Ar.indptr.dtype and A.indices.dtype == Ar.indices.dtype
+    assert np.array_equal(A.indptr, Ar.indptr) and np.array_equal(A.indices, Ar.indices)
+    assert rel_err(A.data, Ar.data, 1e-12) < rtol
+    assert np.array_equal(np.isnan(l), np.isnan(lr)) and np.array_equal(np.isinf(l), np.isinf(lr))
+    f = np.isfinite(lr)
+    assert np.allclose(l[f], lr[f], rtol=rtol, atol=rtol * 1e-2)
+    assert np.allclose(u, ur, rtol=rtol, atol=rtol * 1e-2)
+
+
+@pytest.mark.parametrize("scp_iter", [0, 1, 2, 9])
+def test_reference_config_matches_oracle(scp_iter):
+    from oracle.oracle_b import CarOracleB
+    from riskaversetrajopt_b200.car.driving import Model
+    s = _seed0()
+    model, ref = Model(50, 'saa', 0.05, samples=s), CarOracleB(*s, 'saa', 0.05)
+    us = model.initial_guess_us_mat() + 0.3 * np.random.RandomState(scp_iter).randn(20, 2)
+    _check(*model.get_constraints_coeffs(us, scp_iter), *ref.get_constraints_coeffs(us, scp_iter))
+
+
+def test_model_constructor_draws_like_the_reference():
+    from riskaversetrajopt_b200.car.driving import Model
+    np.random.seed(0)
+    m = Model(50, 'saa', 0.05)
+    s = _seed0()
+    assert all(np.array_equal(a, b) for a, b in zip(
+        (m.states_init, m.omegas_speed, m.omegas_repulsive, m.DWs), s))
+
+
+def test_golden():
+    from riskaversetrajopt_b200.car.driving import Model
+    g = np.load(os.path.join(G, "car_M50_saa.npz"))
+    model = Model(50, 'saa', 0.05, samples=_seed0())
+    assert np.array_equal(model.initial_guess_us_mat(), g["us0"])
+    for name, us, it in (("iter0", g["us0"], 0), ("iter1", g["us1"], 1), ("iter2", g["us1"], 2)):
+        A, l, u = model.get_constraints_coeffs(us, it)
+        assert A.shape == tuple(g[name + "_shape"])
+        assert np.array_equal(A.indptr, g[name + "_indptr"]) and np.array_equal(A.indices, g[name + "_indices"])
+        assert rel_err(A.data, g[name + "_data"]) < RTOL64
+        assert np.allclose(u, g[name + "_u"], rtol=RTOL64, atol=1e-11)
+        gl = g[name + "_l"]
+        assert np.array_equal(np.isnan(l), np.isnan(gl)) and np.array_equal(np.isinf(l), np.isinf(gl))
+        f = np.isfinite(gl)
+        assert np.allclose(l[f], gl[f], rtol=RTOL64, atol=1e-11)
+    Xs = model.us_to_state_trajectories(g["us1"])
+    assert Xs.shape == (50, 21, 8)
+    assert np.allclose(Xs[:3], g["Xs_first3"], rtol=1e-11, atol=1e-12)
+    sat, Z = model.monte_carlo_constraints(g["us1"])
+    assert np.allclose(Z, g["Z"], rtol=RTOL64, atol=1e-11)
+
+
+def test_baseline_method():
+    from oracle.oracle_b import CarOracleB
+    from riskaversetrajopt_b200.car.driving import Model
+    s = _seed0(20, 'baseline')
+    model, ref = Model(20, 'baseline', 0.05, samples=s), CarOracleB(*s, 'baseline', 0.05)
+    us = model.initial_guess_us_mat() + 0.2 * np.random.RandomState(1).randn(20, 2)
+    _check(*model.get_constraints_coeffs(us, 1), *ref.get_constraints_coeffs(us, 1))
+
+
+@pytest.mark.parametrize("M", [3, 15, 16, 17, 33, 200])
+def test_ragged_sample_counts(M):
+    from oracle.oracle_b import CarOracleB
+    from riskaversetrajopt_b200.car.driving import Model
+    s = tuple(x[:M] for x in _seed0(200))
+    model, ref = Model(M, 'saa', 0.1, samples=s), CarOracleB(*s, 'saa', 0.1)
+    us = model.initial_guess_us_mat() + np.random.RandomState(M).randn(20, 2)
+    for it in (0, 1):
+        _check(*model.get_constraints_coeffs(us, it), *ref.get_constraints_coeffs(us, it))
+    assert np.allclose(model.us_to_state_trajectories(us), ref.rollout(us), rtol=1e-11, atol=1e-12)
+
+
+def test_iteration_order_0_1_2_and_back():
+    from oracle.oracle_b import CarOracleB
+    from riskaversetrajopt_b200.car.driving import Model
+    s = tuple(x[:10] for x in _seed0())
+    model, ref = Model(10, 'saa', 0.05, samples=s), CarOracleB(*s, 'saa', 0.05)
+    us = model.initial_guess_us_mat()
+    for it in (0, 1, 2, 0, 3):
+        _check(*model.get_constraints_coeffs(us, it), *ref.get_constraints_coeffs(us, it))
+
+
+def test_ego_state_must_be_shared():
+    from riskaversetrajopt_b200._lib import SaaError
+    from riskaversetrajopt_b200.car.driving import Model
+    s = list(_seed0(8))
+    s[0] = s[0].copy(); s[0][3, 0] += 1.0
+    with pytest.raises(SaaError):
+        Model(8, 'saa', 0.05, samples=tuple(s))
+
+
+def test_fp32_mode_within_1e4():
+    from oracle.oracle_b import CarOracleB
+    from riskaversetrajopt_b200.car.driving import Model
+    s = _seed0()
+    model, ref = Model(50, 'saa', 0.05, samples=s, precision='fp32'), CarOracleB(*s, 'saa', 0.05)
+    us = model.initial_guess_us_mat() + 0.2 * np.random.RandomState(0).randn(20, 2)
+    A, l, u = model.get_constraints_coeffs(us, 2)
+    Ar, lr, ur = ref.get_constraints_coeffs(us, 2)
+    assert np.array_equal(A.indices, Ar.indices)
+    assert np.max(np.abs(A.data - Ar.data)) / np.max(np.abs(Ar.data)) < RTOL32
+    assert np.allclose(u, ur, rtol=RTOL32, atol=RTOL32 * 10)
+
+
+def test_large_M_sampled_parity():
+    import torch
+    from oracle.oracle_b import CarOracleB
+    from riskaversetrajopt_b200.car.driving import Model, sample_uncertain_parameters
+    M = 100_000
+    st = np.random.get_state(); np.random.seed(5)
+    s = sample_uncertain_parameters(M, 'saa'); np.random.set_state(st)
+    model = Model(M, 'saa', 0.05, samples=s)
+    us = model.initial_guess_us_mat() + 0.1 * np.random.RandomState(2).randn(20, 2)
+    b = model.path.assemble(us, 2)
+    Ax, u = b['Ax'].cpu().numpy(), b['u'].cpu().numpy()
+    n_rows, n_cols, indptr, indices = model.path.pattern()
+    assert Ax.size == 423 * M + 159
+    idx = np.unique(np.concatenate([[0, 15, 16, M - 1], np.random.RandomState(0).randint(0, M, 30)]))
+    ref = CarOracleB(*(x[idx] for x in s), 'saa', 0.05)
+    _, _, _, g_du, g_up, g = ref.per_sample(us)
+    row_s0 = 4 + 1 + M
+    for n, i in enumerate(idx):
+        assert rel_err(u[row_s0 + i * 20: row_s0 + (i + 1) * 20], g_up[n]) < RTOL64
+        for j in (0, 7, 18):
+            for c in (0, 1):
+                col, L = j * 2 + c, 19 - j
+                start = indptr[col] + 3 + i * L
+                assert rel_err(Ax[start:start + L], g_du[n, j + 1:, col]) < RTOL64
+                assert np.array_equal(indices[start:start + L], row_s0 + i * 20 + np.arange(j + 1, 20))
+    Zc, out3 = model.path.cvar_terms(us, t_risk=-1.0)
+    Zh = Zc.cpu().numpy()
+    assert np.allclose(Zh[idx], g.max(axis=1) - 3e-4, rtol=1e-10, atol=1e-12)
+    assert np.isclose(out3[0].item(), np.maximum(Zh + 1.0, 0).sum(), rtol=1e-10)
