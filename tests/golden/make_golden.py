@@ -67,6 +67,37 @@ def car():
     np.savez_compressed(os.path.join(HERE, "car_M50_saa.npz"), **out)
 
 
+def hopper():
+    from oracle.oracle_hopper import HopperOracleA
+    from riskaversetrajopt_b200.hopper import hopper as hp     # host-only constants + sampler
+    np.random.seed(1)                                   # hopper/hopper.py:33
+    feats = hp.sample_friction_features(hp.M)           # :70-74 (I, theta, tau), M = 30
+    rs = np.random.RandomState(11)
+    nv = hp.num_vars(hp.M)
+    Z = np.zeros(nv)
+    # a point inside the reference's variable box (:598-620)
+    xs = np.zeros((hp.S + 1, 8))
+    xs[:, 0] = rs.uniform(-0.2, 0.4, hp.S + 1); xs[:, 1] = rs.uniform(0.6, 1.2, hp.S + 1)
+    xs[:, 2] = rs.uniform(-0.5, 0.5, hp.S + 1); xs[:, 3] = rs.uniform(0.5, 1.2, hp.S + 1)
+    xs[:, 4:] = rs.randn(hp.S + 1, 4)
+    us = rs.randn(hp.S, 4) * np.array([1.0, 10.0, 5.0, 20.0])
+    Z[:xs.size] = xs.ravel(); Z[xs.size:xs.size + us.size] = us.ravel()
+    Z[xs.size + us.size:] = rs.uniform(0, 0.3, hp.M + 2)
+    out = dict(Z=Z)
+    for method in ('saa', 'baseline'):
+        a = HopperOracleA(hp.M, method, 0.2, *feats)
+        g = a.g(Z)
+        lam = rs.randn(g.size)
+        J = a.jac(Z)
+        H = a.hess(Z, lam)
+        r, c = np.nonzero(J)
+        hr, hc = np.nonzero(np.tril(H))
+        out.update({method + "_g": g, method + "_lam": lam, method + "_jac_r": r, method + "_jac_c": c,
+                    method + "_jac_v": J[r, c], method + "_hess_r": hr, method + "_hess_c": hc,
+                    method + "_hess_v": H[hr, hc]})
+    np.savez_compressed(os.path.join(HERE, "hopper_M30.npz"), **out)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["drone", "car", "hopper"]
     for name in which:

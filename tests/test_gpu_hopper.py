@@ -1,0 +1,90 @@
+"""Parity of the hopper slip-risk block (values, Jacobian, Hessian) with the oracles."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _feats():
+    from riskaversetrajopt_b200.hopper import hopper as hp
+    st = np.random.get_state(); np.random.seed(1)
+    f = hp.sample_friction_features(hp.M); np.random.set_state(st)
+    return f
+
+
+def _dense(shape, r, c, v):
+    D = np.zeros(shape)
+    np.add.at(D, (r, c), v)
+    return D
+
+
+@pytest.mark.parametrize("method", ["saa", "baseline"])
+def test_golden_values_jacobian_hessian(method):
+    from riskaversetrajopt_b200.hopper import hopper as hp
+    g = np.load(os.path.join(G, "hopper_M30.npz"))
+    Z = g["Z"]
+    m = hp.Model(hp.M, method, 0.2, _feats())
+    nv = hp.num_vars(hp.M)
+    gs = m.slip_risk_constraints(Z)
+    assert gs.shape == g[method + "_g"].shape == (m.n_rows,)
+    assert np.allclose(gs, g[method + "_g"], rtol=1e-9, atol=1e-12)
+    r, c, v = m.slip_risk_jacobian(Z)
+    J = _dense((m.n_rows, nv), r, c, v)
+    Jg = _dense((m.n_rows, nv), g[method + "_jac_r"], g[method + "_jac_c"], g[method + "_jac_v"])
+    assert np.allclose(J, Jg, rtol=1e-9, atol=1e-12)
+    # the structural pattern covers every non-zero the reference's dense jacrev has
+    assert set(zip(g[method + "_jac_r"], g[method + "_jac_c"])) <= set(zip(r, c))
+    hr, hc, hv = m.slip_risk_hessian(Z, g[method + "_lam"])
+    assert np.all(hr >= hc)
+    H = _dense((nv, nv), hr, hc, hv)
+    Hg = _dense((nv, nv), g[method + "_hess_r"], g[method + "_hess_c"], g[method + "_hess_v"])
+    assert np.allclose(H, Hg, rtol=1e-9, atol=1e-11)
+
+
+def test_callback_style_helpers_match_dense_oracle():
+    from oracle.oracle_hopper import HopperOracleA
+    from riskaversetrajopt_b200.hopper import hopper as hp
+    M = 7
+    rs = np.random.RandomState(3)
+    f = tuple(x[:M] for x in _feats())
+    nv = hp.num_vars(M)
+    Z = rs.uniform(-1, 1, nv); Z[3::8][:31] = rs.uniform(0.5, 1.2, 31)
+    m, a = hp.Model(M, 'saa', 0.3, f), HopperOracleA(M, 'saa', 0.3, *f)
+    off = 5
+    out = np.full(off + m.n_rows + 3, 7.0)
+    m.eval_g_into(Z, out, off)
+    assert np.allclose(out[off:off + m.n_rows], a.g(Z), rtol=1e-9, atol=1e-12) and out[0] == 7.0 and out[-1] == 7.0
+    Jd = np.full((off + m.n_rows, nv), 1.0)
+    m.eval_jac_g_into(Z, Jd, off)
+    assert np.allclose(Jd[off:], a.jac(Z), rtol=1e-9, atol=1e-12) and np.all(Jd[:off] == 1.0)
+    lam = rs.randn(m.n_rows)
+    Hd = np.zeros((nv, nv))
+    m.eval_h_add(Z, lam, Hd)
+    assert np.allclose(Hd, a.hess(Z, lam), rtol=1e-9, atol=1e-11)
+
+
+def test_large_M_and_fp32():
+    from oracle.oracle_hopper import HopperOracleB
+    from riskaversetrajopt_b200.hopper import hopper as hp
+    M = 50_000
+    rs = np.random.RandomState(5)
+    f = (0.025 * np.sqrt(2 / 30) * rs.uniform(0, 1, (M, 30)), rs.uniform(0, np.pi, (M, 30)),
+         rs.uniform(0, 2 * np.pi, (M, 30)))
+    Z = rs.uniform(-1, 1, hp.num_vars(M))
+    m = hp.Model(M, 'saa', 0.1, f)
+    b = HopperOracleB(M, 'saa', 0.1, *f)
+    assert np.allclose(m.slip_risk_constraints(Z), b.g(Z), rtol=1e-9, atol=1e-12)
+    # Hessian sums: sum_i lam mu', sum_i lam mu'' against the closed form
+    px, fx, fz, x2, x3 = m._contact_geometry(Z)
+    lam = rs.randn(M, 20)
+    _, dmu, hs = m._friction(px, lam.reshape(-1))
+    mu_b, dmu_b, d2mu_b = b.friction(px)
+    assert np.allclose(dmu, dmu_b, rtol=1e-9, atol=1e-13)
+    assert np.allclose(hs[:, 0], (lam * dmu_b).sum(0), rtol=1e-9, atol=1e-10)
+    assert np.allclose(hs[:, 1], (lam * d2mu_b).sum(0), rtol=1e-9, atol=1e-10)
+    m32 = hp.Model(M, 'saa', 0.1, f, precision='fp32')
+    g32 = m32.slip_risk_constraints(Z)
+    assert np.allclose(g32, b.g(Z), rtol=1e-4, atol=1e-4)
