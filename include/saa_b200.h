@@ -171,6 +171,19 @@ int64_t saa_mean_len(const saa_handle *h);
 int saa_finalize_means(saa_handle *h, const double *mean_sums_dev, int scp_iter,
                        void *Ax_dev, void *l_dev, void *u_dev, void *stream);
 
+/*
+ * Multi-GPU gather, NCCL variant: after the ranks' compact value blocks (a matrix of
+ * M_shard samples each, i.e. what saa_linearize_assemble writes under
+ * saa_set_output_geometry(M_shard, 0)) have been gathered into rank 0's memory,
+ * copy one shard's per-iteration values -- the sub-run of every u column and the
+ * sample rows' upper bounds -- to their place in the destination matrix of `h`
+ * (M_out samples), starting at sample `first`.  Pure device-to-device copies.
+ * (The fused alternative needs no call: pass peer-mapped Ax/u pointers of rank
+ * 0's buffers to saa_linearize_assemble under the global geometry.)
+ */
+int saa_merge_shard(saa_handle *h, const void *shard_Ax_dev, const void *shard_u_dev,
+                    int64_t M_shard, int64_t first, void *Ax_dev, void *u_dev, void *stream);
+
 /* Rollout only: Xs_dev (M_local, S+1, n_x) row-major.
  * replaces: Model.us_to_state_trajectories (drone/drone_risk.py:157-162,
  *           car/driving.py:207-214).                                          */

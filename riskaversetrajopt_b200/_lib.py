@@ -63,6 +63,8 @@ _PROTOTYPES = {
     "saa_mean_len": (C.c_int64, [_H]),
     "saa_finalize_means": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p]),
+    "saa_merge_shard": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
+                                  C.c_void_p, C.c_void_p]),
     "saa_rollout": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p]),
     "saa_cvar_terms": (C.c_int, [_H, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p,
                                  C.c_void_p]),

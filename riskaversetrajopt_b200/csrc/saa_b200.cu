@@ -341,6 +341,52 @@ int launch_finalize(saa_handle *h, const double *sums, int relaxed_pattern, void
   return SAA_OK;
 }
 
+// ---------------------------------------------------------------------------
+// merge a gathered compact shard into the destination matrix (multi-GPU, NCCL path)
+// ---------------------------------------------------------------------------
+struct MergeArgs {
+  int ncols;
+  i64 src_off[64], dst_off[64], count[64];   // u columns that carry sample rows, then the bounds
+};
+
+template <typename T>
+__global__ void merge_shard_kernel(const __grid_constant__ MergeArgs G, const T *__restrict__ sAx,
+                                   const T *__restrict__ su, T *__restrict__ Ax, T *__restrict__ u) {
+  // blockIdx.y = run, blockIdx.x strides over the run
+  const int r = blockIdx.y;
+  const bool bounds = (r == G.ncols - 1);
+  const T *src = (bounds ? su : sAx) + G.src_off[r];
+  T *dst = (bounds ? u : Ax) + G.dst_off[r];
+  const i64 n = G.count[r];
+  for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (i64)gridDim.x * blockDim.x)
+    dst[e] = src[e];
+}
+
+template <typename T>
+int launch_merge(saa_handle *h, const void *sAx, const void *su, i64 M_shard, i64 first, void *Ax,
+                 void *u, cudaStream_t st) {
+  const Layout &L = h->lay;
+  Layout Ls; Ls.build(h->problem, h->method, h->S, M_shard, false);
+  MergeArgs G{};
+  int n = 0;
+  for (int c = 0; c < L.nu; ++c) {
+    const int len = L.run_len(c);
+    if (len == 0) continue;
+    if (n >= 63) return fail(h, SAA_ERR_ARG, "too many columns");
+    G.src_off[n] = Ls.run_start(c);
+    G.dst_off[n] = L.run_start(c) + first * len;
+    G.count[n] = M_shard * len;
+    ++n;
+  }
+  G.src_off[n] = Ls.row_s0; G.dst_off[n] = L.row_s0 + first * L.R; G.count[n] = M_shard * L.R;
+  G.ncols = ++n;
+  const int threads = 256;
+  const int bx = (int)std::max<i64>(1, std::min<i64>((M_shard * 57 + threads - 1) / threads, (i64)h->n_sms * 2));
+  merge_shard_kernel<T><<<dim3(bx, n), threads, 0, st>>>(G, (const T *)sAx, (const T *)su, (T *)Ax, (T *)u);
+  SAA_CUDA(h, cudaGetLastError());
+  return SAA_OK;
+}
+
 }  // namespace
 
 #include "car_host.cuh"
@@ -555,6 +601,18 @@ int saa_linearize_assemble(saa_handle *h, const double *us, int scp_iter, void *
   if (rc) return rc;
   if (finalize) return saa_finalize_means(h, sums, scp_iter, Ax, l, u, stream);
   return SAA_OK;
+}
+
+int saa_merge_shard(saa_handle *h, const void *shard_Ax, const void *shard_u, int64_t M_shard,
+                    int64_t first, void *Ax, void *u, void *stream) {
+  if (!h || !shard_Ax || !shard_u || !Ax || !u) return fail(h, SAA_ERR_ARG, "NULL argument");
+  if (h->problem == SAA_HOPPER) return fail(h, SAA_ERR_ARG, "hopper has no QP matrix");
+  if (M_shard < 1 || first < 0 || first + M_shard > h->M_out)
+    return fail(h, SAA_ERR_ARG, "shard does not fit the destination geometry");
+  SAA_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  return h->precision == 64 ? launch_merge<double>(h, shard_Ax, shard_u, M_shard, first, Ax, u, st)
+                            : launch_merge<float>(h, shard_Ax, shard_u, M_shard, first, Ax, u, st);
 }
 
 int saa_rollout(saa_handle *h, const double *us, void *Xs, void *stream) {

@@ -1,0 +1,181 @@
+"""Sample sharding across the GPUs of one box (one process per GPU, ``torch.distributed``).
+
+The reference is single-process; its only cross-sample operations are the sample
+means of the final-state rows (``jnp.mean(..., axis=0)``, drone/drone_risk.py:294-296,
+car/driving.py:311-313).  Everything else is independent per sample, so rank ``r``
+owns the contiguous sample block ``shard_range(M, W, r)`` and with it a contiguous
+sub-run of every sample-carrying CSC column.
+
+Per SCP iteration:
+  1. ``us`` (<= 60 doubles) is broadcast from rank 0;
+  2. every rank runs ``saa_linearize_assemble`` on its block;
+  3. ``all_reduce(sum)`` of the mean-row partial sums (123 / 120 doubles, NCCL);
+  4. delivery of the row blocks, one of
+     * ``'sharded'``  – blocks stay in their owners' HBM (compact matrices),
+     * ``'peer'``     – fused gather: every rank's kernel stores straight into rank
+       0's global value arrays through peer-mapped (CUDA IPC / NVLink) pointers,
+     * ``'nccl'``     – ``gather`` of the compact blocks to rank 0 followed by
+       ``saa_merge_shard`` (device-to-device run copies).
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from ._lib import lib, check
+
+
+def shard_range(M, world, rank):
+    """Balanced contiguous blocks: -> (first sample, sample count) of ``rank``."""
+    M, world, rank = int(M), int(world), int(rank)
+    if not (0 <= rank < world) or M < world:
+        raise ValueError("need 0 <= rank < world <= M")
+    base, rem = divmod(M, world)
+    first = rank * base + min(rank, rem)
+    return first, base + (1 if rank < rem else 0)
+
+
+def broadcast_controls(us_mat, src=0, group=None, device=None):
+    """Rank ``src``'s iterate to every rank (host array in, host array out)."""
+    t = torch.as_tensor(np.ascontiguousarray(us_mat, dtype=np.float64))
+    if device is not None:
+        t = t.to(device)
+    dist.broadcast(t, src=src, group=group)
+    return t.cpu().numpy()
+
+
+def all_reduce_sums(t, group=None):
+    """Sum of the per-rank partial sums (the ``mean`` is taken by ``saa_finalize_means``)."""
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
+def _share_tensor(t, src, group=None):
+    """Map rank ``src``'s CUDA tensor into every process (CUDA IPC; NVLink peer access).
+    Returns a tensor aliasing the same device memory."""
+    from torch.multiprocessing.reductions import reduce_tensor
+    rank = dist.get_rank(group)
+    payload = [reduce_tensor(t) if rank == src else None]
+    dist.broadcast_object_list(payload, src=src, group=group)
+    if rank == src:
+        return t
+    rebuild, args = payload[0]
+    return rebuild(*args)
+
+
+class ShardedAssembler:
+    """Drives one ``DevicePath`` per rank.  ``path`` must have been created with
+    ``M_local, M_global, sample_offset = shard_range(...)``-consistent arguments."""
+
+    def __init__(self, path, mode='sharded', group=None):
+        if mode not in ('sharded', 'peer', 'nccl'):
+            raise ValueError("mode must be 'sharded', 'peer' or 'nccl'")
+        self.path, self.mode, self.group = path, mode, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.out = None
+        if mode in ('sharded', 'nccl'):
+            path.set_output_geometry(path.M_local, 0)
+        else:
+            path.set_output_geometry(path.M_global, path.sample_offset)
+        if mode == 'peer':
+            self._setup_peer()
+        if mode == 'nccl':
+            self._setup_nccl()
+
+    # -- fused gather: rank 0 owns the global arrays, everybody maps them -------------
+    def _setup_peer(self):
+        p = self.path
+        if self.rank == 0:
+            b = p.buffers(False)
+            mine = (b['Ax'], b['l'], b['u'])
+        else:
+            mine = (None, None, None)
+        shared = [_share_tensor(t, 0, self.group) for t in mine]
+        self._peer_keep = shared
+        self.out = dict(Ax=shared[0].data_ptr(), l=shared[1].data_ptr(), u=shared[2].data_ptr(),
+                        const_state=None)
+        if self.rank == 0:
+            self.out = p.buffers(False)
+
+    def _setup_nccl(self):
+        p = self.path
+        counts = [torch.zeros(1, dtype=torch.int64, device=p.device) for _ in range(self.world)]
+        dist.all_gather(counts, torch.tensor([p.M_local], dtype=torch.int64, device=p.device),
+                        group=self.group)
+        self.counts = [int(c.item()) for c in counts]
+        if len(set(self.counts)) != 1:
+            raise ValueError("mode='nccl' gathers equal shards: M must be divisible by the world size")
+        if self.rank == 0:
+            from .device_path import DevicePath
+            # a second handle on rank 0 describing the GLOBAL matrix: pattern, constant
+            # entries, merge offsets, mean rows.  It needs the problem constants
+            # (bind_global_params) but no samples.
+            self.global_path = DevicePath(p.problem, p.method, p.S, p.alpha, p.M_global,
+                                          M_global=p.M_global, sample_offset=0, variant=p.variant,
+                                          precision='fp64' if p.bits == 64 else 'fp32',
+                                          device=p.device.index)
+
+    def bind_global_params(self, setter):
+        """``setter(path)`` sets the problem constants (``set_params_drone`` / ``_car``) on rank
+        0's global-geometry handle; call once after construction in ``mode='nccl'``."""
+        if self.mode == 'nccl' and self.rank == 0:
+            setter(self.global_path)
+
+    # -- one SCP iteration ---------------------------------------------------------------
+    def step(self, us_mat, scp_iter):
+        p = self.path
+        us = broadcast_controls(us_mat, 0, self.group, device=p.device if dist.get_backend(self.group) == 'nccl' else None)
+        b = p.assemble(us, scp_iter, finalize=False, write_shared=(self.rank == 0 or self.mode != 'peer'),
+                       out=self.out)
+        all_reduce_sums(p.mean_sums, self.group)
+        if self.mode == 'peer':
+            # remote stores must have landed before rank 0 consumes the arrays
+            torch.cuda.current_stream(p.device).synchronize()
+            dist.barrier(group=self.group)
+            if self.rank == 0:
+                p.finalize_means(b, scp_iter)
+            return b if self.rank == 0 else None
+        p.finalize_means(b, scp_iter)
+        if self.mode == 'sharded':
+            return b
+        return self._gather_nccl(b, scp_iter)
+
+    def _gather_nccl(self, b, scp_iter):
+        p = self.path
+        n_rows, _, nnz = p.pattern_sizes(False)
+        n_var = self._n_var(p)
+        sendA, sendu = b['Ax'][:n_var], b['u']
+        if self.rank == 0:
+            recvA = [torch.empty_like(sendA) for _ in range(self.world)]
+            recvu = [torch.empty_like(sendu) for _ in range(self.world)]
+        else:
+            recvA = recvu = None
+        dist.gather(sendA, recvA, dst=0, group=self.group)
+        dist.gather(sendu, recvu, dst=0, group=self.group)
+        if self.rank != 0:
+            return None
+        g = self.global_path
+        gb = g.buffers(False)
+        relaxed = scp_iter < g.relax_threshold()
+        if gb.get('const_state') != relaxed:
+            # rank 0 writes every constant entry of the global matrix (once per relaxation state)
+            check(lib.saa_write_constants(g.handle, int(scp_iter), 1, gb['Ax'].data_ptr(),
+                                          gb['l'].data_ptr(), gb['u'].data_ptr(), g._stream()), g.handle)
+            gb['const_state'] = relaxed
+        first = 0
+        for r in range(self.world):
+            check(lib.saa_merge_shard(g.handle, recvA[r].data_ptr(), recvu[r].data_ptr(), self.counts[r],
+                                      first, gb['Ax'].data_ptr(), gb['u'].data_ptr(), g._stream()), g.handle)
+            first += self.counts[r]
+        g.mean_sums.copy_(p.mean_sums)
+        g.finalize_means(gb, scp_iter)
+        return gb
+
+    @staticmethod
+    def _n_var(p):
+        """Length of the leading u-column block of A.data (everything before the y columns):
+        per sample 1140 (drone) / 380 (car) Jacobian entries, plus the final-row and
+        control-row entries (117 + 60 / 116 + 40)."""
+        from . import _lib
+        if p.problem == _lib.SAA_DRONE:
+            return 1140 * p.M_out + 177
+        return 380 * p.M_out + 156

@@ -1,0 +1,108 @@
+"""2-rank NCCL runs of the sharded path (skipped on a single-GPU box): every delivery
+mode must reproduce the single-GPU matrix."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, initfile, M, problem, out):
+    import torch
+    import torch.distributed as dist
+    from riskaversetrajopt_b200 import _lib, dist as sd
+    from riskaversetrajopt_b200.device_path import DevicePath
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"file://{initfile}", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    rs = np.random.RandomState(0)
+    if problem == 'drone':
+        from riskaversetrajopt_b200.drone import drone_params as dp
+        from riskaversetrajopt_b200.drone.drone_utils import sample_uncertain_parameters
+        np.random.seed(0)
+        DWs, masses, obs_Qs = sample_uncertain_parameters('saa', M=M)
+        us = rs.randn(20, 3)
+        pid, its = _lib.SAA_DRONE, (0, 2, 3)
+
+        def make(first, cnt, M_global):
+            p = DevicePath(pid, 'saa', 20, 0.1, cnt, M_global=M_global, sample_offset=first, device=rank)
+            p.set_params_drone(dp, dp.OSQP_TOL)
+            p.set_samples_drone(masses[first:first + cnt], DWs[first:first + cnt], obs_Qs[first:first + cnt])
+            return p
+        setp = lambda p: p.set_params_drone(dp, dp.OSQP_TOL)
+    else:
+        from riskaversetrajopt_b200.car import driving_params as cp
+        from riskaversetrajopt_b200.car.driving import sample_uncertain_parameters, BETA
+        np.random.seed(0)
+        s = sample_uncertain_parameters(M, 'saa')
+        us = 0.01 + 0.3 * rs.randn(20, 2)
+        pid, its = _lib.SAA_CAR, (1, 2)
+
+        def make(first, cnt, M_global):
+            p = DevicePath(pid, 'saa', 20, 0.05, cnt, M_global=M_global, sample_offset=first, device=rank)
+            p.set_params_car(cp, BETA, cp.OSQP_TOL)
+            p.set_samples_car(*(x[first:first + cnt] for x in s))
+            return p
+        setp = lambda p: p.set_params_car(cp, BETA, cp.OSQP_TOL)
+
+    res = {}
+    first, cnt = sd.shard_range(M, world, rank)
+    for mode in ('sharded', 'peer', 'nccl'):
+        path = make(first, cnt, M)
+        asm = sd.ShardedAssembler(path, mode=mode)
+        asm.bind_global_params(setp)
+        for it in its:
+            b = asm.step(us if rank == 0 else np.zeros_like(us), it)
+            torch.cuda.synchronize()
+            dist.barrier()
+            if b is not None:
+                res[(mode, it, rank)] = tuple(b[k].cpu().numpy() for k in ('Ax', 'l', 'u'))
+        del asm, path
+    if rank == 0:
+        single = make(0, M, M)
+        for it in its:
+            b = single.assemble(us, it)
+            res[('single', it, 0)] = tuple(b[k].cpu().numpy() for k in ('Ax', 'l', 'u'))
+        if problem == 'drone':
+            res['pattern'] = single.pattern()[2]
+    out[rank] = res
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("problem,M", [("drone", 1000), ("car", 1000), ("drone", 37)])
+def test_two_ranks_reproduce_single_gpu(problem, M):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    mgr = mp.Manager()
+    out = mgr.dict()
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_worker, args=(2, os.path.join(d, "init"), M, problem, out), nprocs=2, join=True)
+    r0, r1 = out[0], out[1]
+    its = (0, 2, 3) if problem == 'drone' else (1, 2)
+    per, fixed = (1140, 177) if problem == 'drone' else (380, 156)
+    R = 60 if problem == 'drone' else 20
+    nfin = 6 if problem == 'drone' else 4
+    for it in its:
+        Ax, l, u = r0[('single', it, 0)]
+        for mode in ('peer', 'nccl'):
+            if mode == 'nccl' and M % 2:
+                continue
+            gAx, gl, gu = r0[(mode, it, 0)]
+            # u-column block, bounds and the mean rows: same kernel, same samples -> bitwise, except
+            # the mean rows (different summation order across ranks)
+            assert np.allclose(gAx, Ax, rtol=1e-12, atol=1e-14), (mode, it)
+            body = slice(nfin, None)
+            assert np.array_equal(gu[body], u[body]) and np.array_equal(gl[body], l[body])
+            assert np.allclose(gu[:nfin], u[:nfin], rtol=1e-12, atol=1e-14)
+        # sharded: each rank's compact block equals the corresponding rows of the global problem
+        M0 = (M + 1) // 2
+        for rank, res, first, cnt in ((0, r0, 0, M0), (1, r1, M0, M - M0)):
+            sAx, sl, su = res[('sharded', it, rank)]
+            assert sAx.size == (per + (R + 2) + 1 + R) * cnt + fixed + 3
+            row_s0_g, row_s0_s = nfin + 1 + M, nfin + 1 + cnt
+            assert np.array_equal(su[row_s0_s:row_s0_s + cnt * R], u[row_s0_g + first * R:row_s0_g + (first + cnt) * R])
+            assert np.allclose(su[:nfin], u[:nfin], rtol=1e-12, atol=1e-14)      # global means on every rank
