@@ -184,6 +184,19 @@ int saa_finalize_means(saa_handle *h, const double *mean_sums_dev, int scp_iter,
 int saa_merge_shard(saa_handle *h, const void *shard_Ax_dev, const void *shard_u_dev,
                     int64_t M_shard, int64_t first, void *Ax_dev, void *u_dev, void *stream);
 
+/*
+ * Peer-mapped buffers for the fused multi-GPU gather (one process per GPU).  The
+ * owner allocates with saa_shared_alloc (plain cudaMalloc on `device`) and sends the
+ * 64-byte handle to the other processes (any host channel, e.g. torch.distributed);
+ * they map it with saa_shared_open while THEIR device is current, which enables
+ * NVLink peer access lazily, and pass the returned pointer as Ax/l/u to
+ * saa_write_constants / saa_linearize_assemble under the global output geometry.
+ */
+int saa_shared_alloc(int device, int64_t bytes, void **ptr_out, unsigned char handle_out[64]);
+int saa_shared_open(int device, const unsigned char handle[64], void **ptr_out);
+int saa_shared_close(int device, void *ptr);
+int saa_shared_free(int device, void *ptr);
+
 /* Rollout only: Xs_dev (M_local, S+1, n_x) row-major.
  * replaces: Model.us_to_state_trajectories (drone/drone_risk.py:157-162,
  *           car/driving.py:207-214).                                          */

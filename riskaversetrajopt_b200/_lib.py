@@ -65,6 +65,10 @@ _PROTOTYPES = {
                                      C.c_void_p]),
     "saa_merge_shard": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
                                   C.c_void_p, C.c_void_p]),
+    "saa_shared_alloc": (C.c_int, [C.c_int, C.c_int64, C.POINTER(C.c_void_p), C.c_char_p]),
+    "saa_shared_open": (C.c_int, [C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]),
+    "saa_shared_close": (C.c_int, [C.c_int, C.c_void_p]),
+    "saa_shared_free": (C.c_int, [C.c_int, C.c_void_p]),
     "saa_rollout": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p]),
     "saa_cvar_terms": (C.c_int, [_H, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p,
                                  C.c_void_p]),

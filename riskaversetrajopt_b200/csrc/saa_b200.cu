@@ -615,6 +615,43 @@ int saa_merge_shard(saa_handle *h, const void *shard_Ax, const void *shard_u, in
                             : launch_merge<float>(h, shard_Ax, shard_u, M_shard, first, Ax, u, st);
 }
 
+int saa_shared_alloc(int device, int64_t bytes, void **ptr_out, unsigned char handle_out[64]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  if (!ptr_out || !handle_out || bytes <= 0) return fail(nullptr, SAA_ERR_ARG, "bad argument");
+  if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, SAA_ERR_CUDA, "cudaSetDevice failed");
+  void *p = nullptr;
+  cudaError_t e = cudaMalloc(&p, (size_t)bytes);
+  if (e != cudaSuccess) return fail(nullptr, SAA_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  cudaIpcMemHandle_t hd;
+  e = cudaIpcGetMemHandle(&hd, p);
+  if (e != cudaSuccess) { cudaFree(p); return fail(nullptr, SAA_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e)); }
+  std::memcpy(handle_out, &hd, 64);
+  *ptr_out = p;
+  return SAA_OK;
+}
+
+int saa_shared_open(int device, const unsigned char handle[64], void **ptr_out) {
+  if (!ptr_out || !handle) return fail(nullptr, SAA_ERR_ARG, "bad argument");
+  if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, SAA_ERR_CUDA, "cudaSetDevice failed");
+  cudaIpcMemHandle_t hd;
+  std::memcpy(&hd, handle, 64);
+  void *p = nullptr;
+  cudaError_t e = cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) return fail(nullptr, SAA_ERR_CUDA, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+  *ptr_out = p;
+  return SAA_OK;
+}
+
+int saa_shared_close(int device, void *ptr) {
+  if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, SAA_ERR_CUDA, "cudaSetDevice failed");
+  return cudaIpcCloseMemHandle(ptr) == cudaSuccess ? SAA_OK : fail(nullptr, SAA_ERR_CUDA, "cudaIpcCloseMemHandle failed");
+}
+
+int saa_shared_free(int device, void *ptr) {
+  if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, SAA_ERR_CUDA, "cudaSetDevice failed");
+  return cudaFree(ptr) == cudaSuccess ? SAA_OK : fail(nullptr, SAA_ERR_CUDA, "cudaFree failed");
+}
+
 int saa_rollout(saa_handle *h, const double *us, void *Xs, void *stream) {
   if (!h || !us || !Xs) return fail(h, SAA_ERR_ARG, "NULL argument");
   if (h->problem == SAA_HOPPER) return fail(h, SAA_ERR_ARG, "the hopper trajectory is a decision variable");

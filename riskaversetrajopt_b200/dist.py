@@ -49,17 +49,47 @@ def all_reduce_sums(t, group=None):
     return t
 
 
-def _share_tensor(t, src, group=None):
-    """Map rank ``src``'s CUDA tensor into every process (CUDA IPC; NVLink peer access).
-    Returns a tensor aliasing the same device memory."""
-    from torch.multiprocessing.reductions import reduce_tensor
-    rank = dist.get_rank(group)
-    payload = [reduce_tensor(t) if rank == src else None]
-    dist.broadcast_object_list(payload, src=src, group=group)
-    if rank == src:
-        return t
-    rebuild, args = payload[0]
-    return rebuild(*args)
+class _DeviceArray:
+    """Wraps a raw device pointer for ``torch.as_tensor`` (``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr, n, np_dtype):
+        self.__cuda_array_interface__ = dict(shape=(int(n),), typestr=np.dtype(np_dtype).str,
+                                             data=(int(ptr), False), version=3)
+
+
+class SharedBuffers:
+    """Rank ``src`` owns cudaMalloc'ed (Ax, l, u); every other rank maps them over NVLink
+    (CUDA IPC, opened with the mapping rank's GPU current)."""
+
+    def __init__(self, sizes, np_dtype, device, src=0, group=None):
+        import ctypes as C
+        self.device, self.src = device, src
+        self.rank = dist.get_rank(group)
+        self.owner = self.rank == src
+        esz = np.dtype(np_dtype).itemsize
+        self.ptrs, handles = [], []
+        if self.owner:
+            for n in sizes:
+                ptr, hd = C.c_void_p(), C.create_string_buffer(64)
+                check(lib.saa_shared_alloc(device.index, int(n) * esz, C.byref(ptr), hd))
+                self.ptrs.append(ptr.value)
+                handles.append(hd.raw)
+        payload = [handles]
+        dist.broadcast_object_list(payload, src=src, group=group)
+        if not self.owner:
+            for hd in payload[0]:
+                ptr = C.c_void_p()
+                check(lib.saa_shared_open(device.index, hd, C.byref(ptr)))
+                self.ptrs.append(ptr.value)
+        self.tensors = None
+        if self.owner:
+            self.tensors = [torch.as_tensor(_DeviceArray(p, n, np_dtype), device=device)
+                            for p, n in zip(self.ptrs, sizes)]
+
+    def close(self):
+        for p in self.ptrs:
+            (lib.saa_shared_free if self.owner else lib.saa_shared_close)(self.device.index, p)
+        self.ptrs = []
 
 
 class ShardedAssembler:
@@ -84,17 +114,15 @@ class ShardedAssembler:
     # -- fused gather: rank 0 owns the global arrays, everybody maps them -------------
     def _setup_peer(self):
         p = self.path
+        n_rows, _, nnz = p.pattern_sizes(False)
+        npdt = np.float64 if p.bits == 64 else np.float32
+        self.shared = SharedBuffers((nnz, n_rows, n_rows), npdt, p.device, 0, self.group)
         if self.rank == 0:
-            b = p.buffers(False)
-            mine = (b['Ax'], b['l'], b['u'])
+            Ax, l, u = self.shared.tensors
+            self.out = dict(Ax=Ax, l=l, u=u, const_state=None)
         else:
-            mine = (None, None, None)
-        shared = [_share_tensor(t, 0, self.group) for t in mine]
-        self._peer_keep = shared
-        self.out = dict(Ax=shared[0].data_ptr(), l=shared[1].data_ptr(), u=shared[2].data_ptr(),
-                        const_state=None)
-        if self.rank == 0:
-            self.out = p.buffers(False)
+            Ax, l, u = self.shared.ptrs       # raw peer pointers into rank 0's HBM
+            self.out = dict(Ax=Ax, l=l, u=u, const_state=None)
 
     def _setup_nccl(self):
         p = self.path
