@@ -63,50 +63,82 @@ def _traffic():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled DURING the timed region (NVML in a thread, 5 ms
+    period; falls back to `nvidia-smi -lms`)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+               0x4: "sw_power_cap"}
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.sm, self.mask, self.max_mhz = index, [], 0, None
+        self._stop = threading.Event()
+        self.t = None
+        self.mode = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "50"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        self.mask |= int(get_reasons(h))
+                    except Exception:
+                        pass
+                    time.sleep(0.005)
+            self.mode = "nvml"
+            self.t = threading.Thread(target=loop, daemon=True)
             self.t.start()
         except Exception:
-            self.proc = None
+            self._start_smi()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
-
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
+    def _start_smi(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
         try:
-            self.proc.wait(timeout=5)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.mode = "nvidia-smi"
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            inv = {v: k for k, v in self.REASONS.items()}
+
+            def loop():
+                for line in self.proc.stdout:
+                    r = [x.strip() for x in line.split(",")]
+                    try:
+                        self.sm.append(float(r[0])); self.max_mhz = float(r[1])
+                        for n, v in zip(names, r[2:6]):
+                            if v.lower().startswith("active"):
+                                self.mask |= inv[n]
+                    except Exception:
+                        pass
+            self.t = threading.Thread(target=loop, daemon=True)
+            self.t.start()
         except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-                for n, v in zip(names, r[2:6]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
-            except Exception:
-                pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None,
-                "sm_max_mhz": float(max(mx)) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+            self.mode = None
+
+    def mark(self):
+        """number of samples so far (to delimit the timed region)"""
+        return len(self.sm)
+
+    def stop(self, lo=0, hi=None):
+        self._stop.set()
+        if self.mode == "nvidia-smi":
+            self.proc.terminate()
+        if self.t is not None:
+            self.t.join(timeout=2)
+        sm = self.sm[lo:hi] if self.sm[lo:hi] else self.sm
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(n for b, n in self.REASONS.items() if self.mask & b),
+                "samples": len(sm), "source": self.mode,
+                "window": "timed region" if self.sm[lo:hi] else "whole run"}
 
 
 def synthetic_drone_samples(M, seed, device):
@@ -233,20 +265,22 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
     # ---- timed region: K steps, device events on the launching stream -------------
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     barrier()
+    mark_lo = sampler.mark()
     ev[0].record(stream)
     for k in range(args.steps):
         step()
         ev[k + 1].record(stream)
     barrier()
+    mark_hi = sampler.mark()
     total_ms = ev[0].elapsed_time(ev[-1])
     per_step = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
     t = torch.tensor([total_ms], dtype=torch.float64, device=device)
@@ -265,7 +299,7 @@ def run_ours(args):
         b_.record(stream)
     torch.cuda.synchronize()
     kernel_ms = float(np.mean([a.elapsed_time(b_) for a, b_ in kev]))
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(mark_lo, mark_hi) if rank == 0 else None
 
     # ---- e2e through the host-facing call: host us in, pinned host values out ------
     e2e = None
@@ -304,6 +338,15 @@ def run_ours(args):
     except Exception as exc:  # e.g. not enough pinned host memory
         e2e = {"value": None, "unit": UNIT, "error": repr(exc)[:200]}
 
+    # ---- BASELINE target configuration at N > 1: M = 10^6 samples IN TOTAL, row blocks
+    # delivered to rank 0 (fused peer-store gather over NVLink), reported beside the weak-scaling line
+    target = None
+    if world > 1 and not args.no_gather:
+        try:
+            target = measure_target_config(args, rank, world, local_rank, device)
+        except Exception as exc:
+            target = {"error": repr(exc)[:300]}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -337,9 +380,58 @@ def run_ours(args):
         "clocks": clocks,
         "per_step_ms": [round(x, 4) for x in per_step],
     }
+    if target is not None:
+        out["target_config"] = target
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_target_config(args, rank, world, local_rank, device):
+    """M = 10^6 samples in total over `world` GPUs (BASELINE.json target: < 10 ms per SCP
+    iteration on 8 GPUs), for the three delivery modes of riskaversetrajopt_b200.dist."""
+    import torch
+    import torch.distributed as dist
+    from riskaversetrajopt_b200 import _lib, dist as sd
+    from riskaversetrajopt_b200.device_path import DevicePath
+    from riskaversetrajopt_b200.drone import drone_params as dp
+    torch.cuda.empty_cache()
+    M_total = args.target_samples
+    first, cnt = sd.shard_range(M_total, world, rank)
+    us = bench_us()
+    res = {"samples_total": M_total, "n_gpus": world, "unit": "ms per SCP iteration (linearize+assemble)"}
+    for mode in ("sharded", "peer", "nccl"):
+        if mode == "nccl" and M_total % world:
+            continue
+        DWs, masses, obs_Qs = synthetic_drone_samples(cnt, seed=100 + rank, device=device)
+        path = DevicePath(_lib.SAA_DRONE, 'saa', S, 0.1, cnt, M_global=M_total, sample_offset=first,
+                          device=local_rank)
+        path.set_params_drone(dp, dp.OSQP_TOL)
+        path.set_samples_drone(masses, DWs, obs_Qs)
+        torch.cuda.synchronize()
+        del DWs, masses, obs_Qs
+        path._keep = []
+        asm = sd.ShardedAssembler(path, mode=mode)
+        asm.bind_global_params(lambda q: q.set_params_drone(dp, dp.OSQP_TOL))
+        for _ in range(3):
+            asm.step(us, 2)
+        torch.cuda.synchronize(); dist.barrier()
+        n = max(5, min(args.steps, 20))
+        t0 = time.perf_counter()
+        for _ in range(n):
+            asm.step(us, 2)
+        torch.cuda.synchronize(); dist.barrier()
+        t = torch.tensor([(time.perf_counter() - t0) / n], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        res[mode + "_ms"] = float(t.item()) * 1e3
+        if mode == "peer":
+            asm.shared.close()
+        del asm, path
+        torch.cuda.empty_cache()
+    res["note"] = ("host-timed between barriers, max over ranks; 'sharded' leaves row blocks in their owners' HBM, "
+                   "'peer' = kernels store into rank 0's arrays over NVLink (fused gather), "
+                   "'nccl' = gather + merge kernel on rank 0")
+    return res
 
 
 def main():
@@ -351,6 +443,8 @@ def main():
     ap.add_argument("--samples-per-gpu", type=int, default=1_000_000)
     ap.add_argument("--ref-samples", type=int, default=400)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gather", action="store_true")
+    ap.add_argument("--target-samples", type=int, default=1_000_000)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -1,0 +1,71 @@
+"""SCP convergence parity: the same host QP solver driven by GPU-built and by oracle-built
+(P, q, A, l, u) must reach the same trajectory (north_star: "the same converged SCP trajectory")."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+pytestmark = pytest.mark.gpu
+
+
+def _scp(get_coeffs, P, q, us0, iters, reshape):
+    from riskaversetrajopt_b200.qp import make_solver
+    s = make_solver('admm')
+    A, l, u = get_coeffs(us0, 2)
+    s.setup(P, q, A, l, u, eps_abs=1e-5, eps_rel=1e-5, warm_start=True)
+    us, hist = us0, []
+    for it in range(iters):
+        A, l, u = get_coeffs(us, it)
+        s.update(l=l, u=u)
+        s.update(Ax=A.data)
+        r = s.solve()
+        assert r.info.status == 'solved'
+        us = reshape(r.x)
+        hist.append((us, r.x[-1]))
+    return hist
+
+
+def test_drone_scp_same_trajectory(drone_seed0):
+    from oracle.oracle_b import DroneOracleB
+    from riskaversetrajopt_b200.drone import drone_params as dp
+    from riskaversetrajopt_b200.drone.drone_risk import Model
+    DWs, masses, obs_Qs = drone_seed0
+    model = Model(dp.S, DWs, masses, obs_Qs, 'saa', 0.1)
+    ref = DroneOracleB(dp.S, DWs, masses, obs_Qs, 'saa', 0.1)
+    P, q = model.get_objective_coeffs()
+    reshape = lambda x: np.reshape(x[:60], (3, 20), 'F').T
+    us0 = model.initial_guess_us_mat()
+    hg = _scp(model.get_constraints_coeffs, P, q, us0, 8, reshape)
+    hr = _scp(ref.get_constraints_coeffs, P, q, us0, 8, reshape)
+    for (ug, tg), (ur, tr) in zip(hg, hr):
+        assert np.allclose(ug, ur, rtol=1e-6, atol=1e-7) and abs(tg - tr) < 1e-6
+    # and the SCP actually moved away from the initial guess towards the goal
+    Xs = model.us_to_state_trajectories(hg[-1][0])
+    assert np.linalg.norm(Xs[:, -1, :2].mean(axis=0)) < 0.2
+
+
+def test_model_scp_glue_runs(drone_seed0):
+    """define_problem / update_problem / solve as the reference's driver calls them (:506-531)."""
+    from riskaversetrajopt_b200.drone import drone_params as dp
+    from riskaversetrajopt_b200.drone.drone_risk import Model, L2_error_us
+    DWs, masses, obs_Qs = (x[:20] for x in drone_seed0)
+    model = Model(dp.S, DWs, masses, obs_Qs, 'saa', 0.2)
+    us_prev = model.initial_guess_us_mat()
+    model.define_problem(us_prev)
+    for it in range(5):
+        model.update_problem(us_prev, it)
+        us, t_risk = model.solve(verbose=False)
+        err = L2_error_us(us, us_prev)
+        us_prev = us
+    assert us.shape == (20, 3) and np.isfinite(err) and model.res.info.status == 'solved'
+
+
+def test_car_scp_glue_runs():
+    from riskaversetrajopt_b200.car.driving import Model
+    np.random.seed(0)
+    model = Model(20, 'saa', 0.1)
+    us_prev = model.initial_guess_us_mat()
+    for it in range(4):
+        model.define_problem(us_prev, it)
+        us, t_risk = model.solve()
+        us_prev = us
+    assert us.shape == (20, 2) and np.all(np.isfinite(us))
