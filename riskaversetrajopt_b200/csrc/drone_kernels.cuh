@@ -34,7 +34,7 @@
 #define SAA_PAIR 0         // process chains (J, S-2-J) together
 #endif
 #ifndef SAA_COPY
-#define SAA_COPY 0         // 0: simple loop, 1: 8-deep batches inline, 2: shared non-inlined body, 3: TMA bulk stores
+#define SAA_COPY 4         // 0: 8-byte loop, 1: 8-deep batches, 2: non-inlined body, 3: TMA bulk stores, 4: 16-byte vector copy
 #endif
 #ifndef SAA_BPS
 #define SAA_BPS 2          // resident blocks per SM the kernel is compiled for
@@ -101,14 +101,20 @@ __device__ __forceinline__ void drone_chain_step(int k, const T (&P)[S + 1], con
   const int kk = k - J - 1;
 #pragma unroll
   for (int o = 0; o < 3; ++o) {
-    const T coef = q2[o] * (P[k + 1] - oc[o]);     // escale * d g[o,k+1] / d p
+    const T coef = fma(q2[o], P[k + 1], oc[o]);    // escale * d g[o,k+1]/dp = q2 (p - c): oc holds -q2*c
     mine[o * C::L + kk] = coef * c.sp;
   }
 }
 
 template <typename T, int S, int WARPS>
 struct DroneSmem {
-  static constexpr int STAGE = 2 * kTileSamples * (3 * S + 2) + 8;   // elements per warp (>= every Stager<T,LEN>::SIZE)
+  static constexpr int HALF = 2 * kTileSamples * (3 * S + 2) + 8;   // one staging buffer (>= every Stager<T,LEN>::SIZE)
+#if SAA_COPY == 3
+  static constexpr int STAGE = 2 * HALF;   // TMA copy-out is double buffered: the engine drains one
+                                           // column pair while the warp computes the next
+#else
+  static constexpr int STAGE = HALF;
+#endif
   T stage[WARPS][STAGE];
   double wacc[WARPS][DroneRed<S>::N];
 };
@@ -156,8 +162,16 @@ __device__ __forceinline__ void copy_run8(T *__restrict__ dst, const T *__restri
 #endif
 }
 
+// Launch constants the copy-out needs, read from the parameter bank ONCE and pinned in
+// registers (an LDC in front of every column store showed up as long-scoreboard stalls).
+template <typename T> struct DroneOut {
+  T *Ax;
+  i64 mout, first;
+};
+
 template <typename T, int S, int J>
-__device__ __forceinline__ void drone_chain_pairs(const DroneArgs<T, S> &A, const T (&P)[S + 1],
+__device__ __forceinline__ void drone_chain_pairs(const DroneArgs<T, S> &A, const DroneOut<T> &O,
+                                                  const T (&P)[S + 1],
                                                   const T (&A22)[S], const T (&q2)[3],
                                                   const T (&oca)[3], T a21, T dtm, T *stage,
                                                   double *wacc, int a, int si, int lane, i64 s0,
@@ -175,20 +189,32 @@ __device__ __forceinline__ void drone_chain_pairs(const DroneArgs<T, S> &A, cons
     constexpr bool PAIR = (J2 != J);
     // optimisation barriers: keep per-chain coefficient math from being hoisted
     // (common subexpressions across the unrolled chains would cost ~60 live doubles)
-    T q2j[3] = {q2[0], q2[1], q2[2]}, ocj[3] = {oca[0], oca[1], oca[2]};
+    T q2j[3] = {q2[0], q2[1], q2[2]}, ocj[3] = {-q2[0] * oca[0], -q2[1] * oca[1], -q2[2] * oca[2]};
     opaque(q2j[0]); opaque(q2j[1]); opaque(q2j[2]);
     opaque(ocj[0]); opaque(ocj[1]); opaque(ocj[2]);
-#if SAA_COPY == 3
-    static_assert(!SAA_PAIR, "TMA copy-out is implemented for single chains");
+#if SAA_COPY >= 3
+    static_assert(!SAA_PAIR, "TMA / vector copy-out is implemented for single chains");
     using St = Stager<T, C1::LEN>;
-    static_assert(St::SIZE <= DroneSmem<T, S, 1>::STAGE, "staging buffer too small");
-    i64 sbase = s0 + A.first_out, mout = A.M_out;
+    static_assert(St::SIZE <= DroneSmem<T, S, 1>::HALF, "staging buffer too small");
+#if SAA_COPY == 3
+    // upper bounds went through buffer 0, chain 0 takes buffer 1, chain 1 buffer 0, ...
+    T *const stg = stage + ((J & 1) ? 0 : DroneSmem<T, S, 1>::HALF);
+#else
+    T *const stg = stage;
+#endif
+#ifdef SAA_ABL_SAMEADDR
+    i64 sbase = (s0 & 0xfff) + O.first, mout = O.mout;   // ablation (timing only): all tiles hit an L2-resident window
+#else
+    i64 sbase = s0 + O.first, mout = O.mout;
+#endif
     opaque(sbase); opaque(mout);   // recompute the column bases per chain (2 IMADs) instead of keeping 2(S-1) of them live
     const i64 g0 = (a ? C1::CA1 + mout * C1::CB1 : C1::CA0 + mout * C1::CB0) + sbase * C1::LEN;
-    T *mine1 = St::mine(stage, a, si, g0);
+    T *mine1 = St::mine(stg, a, si, g0);
     T *mine2 = mine1;
-    bulk_wait_read();              // the previous column pair has left the staging buffer
+#if SAA_COPY == 3
+    bulk_wait_read1();             // the column pair staged two steps ago has left this buffer
     __syncwarp();
+#endif
 #else
     T *mine1 = stage + (a * kTileSamples + si) * C1::STRIDE;
     T *mine2 = stage + 2 * kTileSamples * C1::STRIDE + (a * kTileSamples + si) * C2::STRIDE;
@@ -196,6 +222,9 @@ __device__ __forceinline__ void drone_chain_pairs(const DroneArgs<T, S> &A, cons
     DroneChainState<T, S> c1{T(0), dtm}, c2{T(0), dtm};   // d(p,v)_{J+1}/du_J = (0, dt/m)
 #pragma unroll
     for (int k = J + 1; k < S; ++k) {
+#ifdef SAA_ABL_NOCHAIN
+      continue;   // ablation (timing only): no chain math, no staging stores
+#endif
       drone_chain_step<T, S, J>(k, P, A22, q2j, ocj, A.dt, a21, mine1, c1);
       if (PAIR && k >= J2 + 1) drone_chain_step<T, S, J2>(k, P, A22, q2j, ocj, A.dt, a21, mine2, c2);
     }
@@ -213,25 +242,34 @@ __device__ __forceinline__ void drone_chain_pairs(const DroneArgs<T, S> &A, cons
 #if SAA_COPY == 3
     fence_async_smem();
     __syncwarp();
-    St::flush(A.Ax, stage, a, si, g0, ns);
+    St::flush(O.Ax, stg, a, si, g0, ns);
+#elif SAA_COPY == 4
+    __syncwarp();
+    {
+      const i64 g0x = C1::CA0 + mout * C1::CB0 + sbase * C1::LEN;
+      const i64 g0y = C1::CA1 + mout * C1::CB1 + sbase * C1::LEN;
+      St::copy_vec(O.Ax, stg, 0, g0x, ns, lane);
+      St::copy_vec(O.Ax, stg, 1, g0y, ns, lane);
+    }
+    __syncwarp();
 #else
     __syncwarp();
-    i64 sbase = s0 + A.first_out, mout = A.M_out;
+    i64 sbase = s0 + O.first, mout = O.mout;
     opaque(sbase); opaque(mout);   // recompute the column bases per chain (2 IMADs) instead of keeping 2(S-1) of them live
-    copy_run8<T, C1::LEN, C1::STRIDE - C1::LEN>(A.Ax + (C1::CA0 + mout * C1::CB0 + sbase * C1::LEN),
+    copy_run8<T, C1::LEN, C1::STRIDE - C1::LEN>(O.Ax + (C1::CA0 + mout * C1::CB0 + sbase * C1::LEN),
                                                 stage, ns * C1::LEN, lane);
-    copy_run8<T, C1::LEN, C1::STRIDE - C1::LEN>(A.Ax + (C1::CA1 + mout * C1::CB1 + sbase * C1::LEN),
+    copy_run8<T, C1::LEN, C1::STRIDE - C1::LEN>(O.Ax + (C1::CA1 + mout * C1::CB1 + sbase * C1::LEN),
                                                 stage + kTileSamples * C1::STRIDE, ns * C1::LEN, lane);
     if (PAIR) {
       const T *st2 = stage + 2 * kTileSamples * C1::STRIDE;
-      copy_run8<T, C2::LEN, C2::STRIDE - C2::LEN>(A.Ax + (C2::CA0 + mout * C2::CB0 + sbase * C2::LEN),
+      copy_run8<T, C2::LEN, C2::STRIDE - C2::LEN>(O.Ax + (C2::CA0 + mout * C2::CB0 + sbase * C2::LEN),
                                                   st2, ns * C2::LEN, lane);
-      copy_run8<T, C2::LEN, C2::STRIDE - C2::LEN>(A.Ax + (C2::CA1 + mout * C2::CB1 + sbase * C2::LEN),
+      copy_run8<T, C2::LEN, C2::STRIDE - C2::LEN>(O.Ax + (C2::CA1 + mout * C2::CB1 + sbase * C2::LEN),
                                                   st2 + kTileSamples * C2::STRIDE, ns * C2::LEN, lane);
     }
     __syncwarp();
 #endif
-    drone_chain_pairs<T, S, J + 1>(A, P, A22, q2, oca, a21, dtm, stage, wacc, a, si, lane, s0, ns,
+    drone_chain_pairs<T, S, J + 1>(A, O, P, A22, q2, oca, a21, dtm, stage, wacc, a, si, lane, s0, ns,
                                    active);
   }
 }
@@ -250,6 +288,15 @@ drone_assemble_kernel(const __grid_constant__ DroneArgs<T, S> A) {
   for (int r = lane; r < Rd::N; r += 32) wacc[r] = 0.0;
   __syncwarp();
 
+  DroneOut<T> O{A.Ax, A.M_out, A.first_out};
+  {
+    i64 ax = (i64)O.Ax;
+    opaque(ax); opaque(O.mout); opaque(O.first);
+    O.Ax = (T *)ax;
+  }
+  i64 ub_base = (i64)A.ub, ub_off = A.ub_off;
+  opaque(ub_base); opaque(ub_off);
+  T *const ub_ptr = (T *)ub_base;
   const i64 ntiles = (A.M + kTileSamples - 1) / kTileSamples;
   const i64 tstride = (i64)gridDim.x * WARPS;
 #pragma unroll 1
@@ -331,12 +378,14 @@ drone_assemble_kernel(const __grid_constant__ DroneArgs<T, S> A) {
       T p = a ? A.x0[1] : A.x0[0], v = a ? A.x0[4] : A.x0[3], tp = T(0), tv = T(0);
       T zmax = -INFINITY;
       P[0] = p;
-#if SAA_COPY == 3
+#if SAA_COPY >= 3
       using StU = Stager<T, 3 * S>;
-      const i64 gu = A.ub_off + s0 * (3 * S);
+      const i64 gu = ub_off + s0 * (3 * S);
       T *ubrow = StU::mine(stage, 0, si, gu);
-      bulk_wait_read();            // last column pair of the previous tile
+#if SAA_COPY == 3
+      bulk_wait_read1();           // buffer 0 was last used by the second-to-last column pair of the previous tile
       __syncwarp();
+#endif
 #else
       T *ubrow = stage + si * (3 * S + 1);
 #endif
@@ -373,17 +422,21 @@ drone_assemble_kernel(const __grid_constant__ DroneArgs<T, S> A) {
 #if SAA_COPY == 3
       fence_async_smem();
       __syncwarp();
-      if (A.ub != nullptr && a == 0) StU::flush(A.ub, stage, 0, si, gu, ns);
+      if (ub_ptr != nullptr && a == 0) StU::flush(ub_ptr, stage, 0, si, gu, ns);
+#elif SAA_COPY == 4
+      __syncwarp();
+      if (ub_ptr != nullptr) StU::copy_vec(ub_ptr, stage, 0, gu, ns, lane);
+      __syncwarp();
 #else
       __syncwarp();
-      if (A.ub != nullptr)
-        copy_run8<T, 3 * S, 1>(A.ub + A.ub_off + s0 * (3 * S), stage, ns * 3 * S, lane);
+      if (ub_ptr != nullptr)
+        copy_run8<T, 3 * S, 1>(ub_ptr + ub_off + s0 * (3 * S), stage, ns * 3 * S, lane);
       __syncwarp();
 #endif
     }
 
     // ---------------- sensitivity chains, two CSC column pairs per pass ---------
-    drone_chain_pairs<T, S, 0>(A, P, A22, q2, oca, a21, dtm, stage, wacc, a, si, lane, s0, ns,
+    drone_chain_pairs<T, S, 0>(A, O, P, A22, q2, oca, a21, dtm, stage, wacc, a, si, lane, s0, ns,
                                active);
   }
 

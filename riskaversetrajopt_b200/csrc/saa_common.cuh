@@ -49,6 +49,9 @@ struct Layout {
 // ----------------------------------------------------------------------------
 template <typename T>
 __device__ __forceinline__ T sum16(T v) {   // sum over the 16 lanes that share lane>>4
+#ifdef SAA_ABL_NOMEAN
+  return v;   // ablation build (timing experiments only): mean rows are wrong
+#endif
   v += __shfl_xor_sync(0xffffffffu, v, 8);
   v += __shfl_xor_sync(0xffffffffu, v, 4);
   v += __shfl_xor_sync(0xffffffffu, v, 2);
@@ -85,7 +88,13 @@ __device__ __forceinline__ void opaque(i64 &v) { asm volatile("" : "+l"(v)); }
 
 // streaming (evict-first) store: assembled values are never re-read by this kernel
 template <typename T>
-__device__ __forceinline__ void st_stream(T *p, T v) { __stcs(p, v); }
+__device__ __forceinline__ void st_stream(T *p, T v) {
+#ifdef SAA_PLAIN_ST
+  *p = v;
+#else
+  __stcs(p, v);
+#endif
+}
 
 // Copy a run of n = n_samples * LEN values, staged in shared memory with row
 // stride STRIDE (>= LEN, odd => conflict-free 64-bit STS from 16 lanes), to a
@@ -114,6 +123,8 @@ __device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, unsigne
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all of this thread's bulk groups have finished READING shared memory (buffer reusable)
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... all but the most recent group (double-buffered staging)
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // make this thread's generic-proxy shared-memory writes visible to the async proxy (TMA)
 __device__ __forceinline__ void fence_async_smem() {
@@ -173,6 +184,63 @@ template <typename T, int LEN> struct Stager {
       for (int e = 0; e < tail; ++e) st_stream(dst + h + bulk + e, run[h + bulk + e]);
     }
     bulk_commit();
+  }
+
+  // Warp-cooperative copy of column a's staged run with 16-byte shared loads and 16-byte
+  // streaming global stores (consecutive lanes -> consecutive 16-byte chunks); the (< VEC)
+  // unaligned head / tail elements of a run or row go out as scalar stores.
+  __device__ __forceinline__ static void copy_vec(T *base, const T *stage, int a, i64 g0, int ns,
+                                                  int lane) {
+#ifdef SAA_ABL_NOCOPY
+    if (ns > 1000) base[g0] = stage[lane];   // ablation build (timing experiments only): no output
+    return;
+#endif
+    const int off = (int)(g0 & (VEC - 1));
+    const int head = (VEC - off) & (VEC - 1);
+    if (ROWWISE) {
+      constexpr int NVMAX = LEN / VEC > 0 ? LEN / VEC : 1;   // vectors per row when off == 0
+      const int nv = (LEN - head) / VEC;                     // LEN % VEC == 0: nv = NVMAX or NVMAX - 1
+      const int tail = LEN - head - nv * VEC;
+      const T *src0 = stage + a * kTileSamples * RSTRIDE + off + head;
+      T *dst0 = base + g0 + head;
+      const int total = ns * nv;
+      constexpr unsigned MAGIC0 = (unsigned)((0x100000000ull + NVMAX - 1) / NVMAX);
+      constexpr unsigned MAGIC1 = NVMAX > 1 ? (unsigned)((0x100000000ull + NVMAX - 2) / (NVMAX - 1)) : 0u;
+      const unsigned magic = head ? MAGIC1 : MAGIC0;
+#pragma unroll 4
+      for (int v = lane; v < total; v += 32) {
+        const int row = (int)__umulhi((unsigned)v, magic);
+        const int idx = v - row * nv;
+        const int4 val = *reinterpret_cast<const int4 *>(src0 + row * RSTRIDE + idx * VEC);
+#ifdef SAA_PLAIN_ST
+        *reinterpret_cast<int4 *>(dst0 + (i64)row * LEN + idx * VEC) = val;
+#else
+        __stcs(reinterpret_cast<int4 *>(dst0 + (i64)row * LEN + idx * VEC), val);
+#endif
+      }
+      if (lane < ns) {
+        const T *row = stage + (a * kTileSamples + lane) * RSTRIDE + off;
+        T *dst = base + g0 + (i64)lane * LEN;
+        for (int e = 0; e < head; ++e) st_stream(dst + e, row[e]);
+        for (int e = 0; e < tail; ++e) st_stream(dst + head + nv * VEC + e, row[head + nv * VEC + e]);
+      }
+    } else {
+      const int n = ns * LEN;
+      const T *run = stage + a * YBASE + off;
+      T *dst = base + g0;
+      const int h = head < n ? head : n;
+      const int nvec = (n - h) / VEC, tail = n - h - nvec * VEC;
+      const int4 *src4 = reinterpret_cast<const int4 *>(run + h);
+      int4 *dst4 = reinterpret_cast<int4 *>(dst + h);
+#pragma unroll 4
+#ifdef SAA_PLAIN_ST
+      for (int v = lane; v < nvec; v += 32) dst4[v] = src4[v];
+#else
+      for (int v = lane; v < nvec; v += 32) __stcs(dst4 + v, src4[v]);
+#endif
+      if (lane < h) st_stream(dst + lane, run[lane]);
+      if (lane < tail) st_stream(dst + h + nvec * VEC + lane, run[h + nvec * VEC + lane]);
+    }
   }
 };
 
