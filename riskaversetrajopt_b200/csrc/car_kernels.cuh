@@ -314,7 +314,13 @@ car_rollout_kernel(const __grid_constant__ CarRollArgs<T, S> A) {
     const T w_s = A.om[s], w_r = A.om[A.Mpad + s];
     T zmax = -INFINITY;
     T *mine = stage + lane * STRIDE;
-#pragma unroll 4
+    T dwx[S], dwy[S];
+#pragma unroll
+    for (int k = 0; k < S; ++k) {
+      dwx[k] = __ldcs(A.dw + (i64)(2 * k) * A.Mpad + s);
+      dwy[k] = __ldcs(A.dw + (i64)(2 * k + 1) * A.Mpad + s);
+    }
+#pragma unroll
     for (int k = 0; k <= S; ++k) {
       if (A.Xs != nullptr) {
 #pragma unroll
@@ -329,8 +335,8 @@ car_rollout_kernel(const __grid_constant__ CarRollArgs<T, S> A) {
         const T sp = w_s * (A.v_des - wy);
         const T fx = fma(-w_r, dx * inv_n, sp), fy = fma(-w_r, dy * inv_n, sp);
         const T nqx = fma(A.dt, wx, qx), nqy = fma(A.dt, wy, qy);
-        wx = wx + A.dt * fx + A.noise_c * A.dw[(i64)(2 * k) * A.Mpad + s];
-        wy = wy + A.dt * fy + A.noise_c * A.dw[(i64)(2 * k + 1) * A.Mpad + s];
+        wx = wx + A.dt * fx + A.noise_c * dwx[k];
+        wy = wy + A.dt * fy + A.noise_c * dwy[k];
         qx = nqx; qy = nqy;
       }
     }

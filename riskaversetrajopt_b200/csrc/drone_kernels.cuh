@@ -526,6 +526,10 @@ drone_rollout_kernel(const __grid_constant__ DroneRollArgs<T, S> A) {
 #pragma unroll
       for (int a = 0; a < 3; ++a) { mine[a] = p[a]; mine[3 + a] = v[a]; }
     }
+    // all noise increments of the sample in flight at once (one DRAM round trip per tile)
+    T dw[S * 3];
+#pragma unroll
+    for (int r = 0; r < S * 3; ++r) dw[r] = __ldcs(A.dw + (i64)r * A.Mpad + s);
 #pragma unroll
     for (int k = 0; k < S; ++k) {
 #pragma unroll
@@ -533,7 +537,7 @@ drone_rollout_kernel(const __grid_constant__ DroneRollArgs<T, S> A) {
         const T absv = fabs(v[a]);
         const T acc = (A.us[k * 3 + a] - A.kp * p[a] - A.kd * v[a] - A.drag * absv * v[a]) * inv_m;
         const T np_ = fma(dt, v[a], p[a]);
-        v[a] = v[a] + dt * acc + nz * A.dw[(k * 3 + a) * A.Mpad + s];
+        v[a] = v[a] + dt * acc + nz * dw[k * 3 + a];
         p[a] = np_;
       }
       if (A.Xs != nullptr) {
