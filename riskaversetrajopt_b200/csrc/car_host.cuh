@@ -1,7 +1,7 @@
 // Host-side launchers of the car kernels (included by saa_b200.cu).
 namespace {
 
-constexpr int kCarWarps = 4;   // 4 warps x 50.9 KB staging = 204 KB shared memory: one block per SM
+constexpr int kCarWarps = SAA_CAR_WARPS;   // one block per SM; shared memory = warps x CarPass::SIZE
 
 // same formula as CarCol<S,J>::CA/CB (car_kernels.cuh)
 i64 car_col_start(int j, int c, int S, i64 M) {

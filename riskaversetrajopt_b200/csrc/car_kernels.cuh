@@ -48,15 +48,6 @@ template <int S, int J> struct CarCol {
   static constexpr int STRIDE = L | 1;
   static constexpr i64 CA0 = 8 * J + 3, CA1 = CA0 + 4;
   static constexpr i64 CB0 = 2 * J * (S - 1) - J * (J - 1), CB1 = CB0 + L;
-  // staging offset (elements) of column (c, J): columns ordered [c][j], 16 rows each
-  static constexpr int prefix() { int s = 0; for (int j = 0; j < J; ++j) s += kTileSamples * ((S - 1 - j) | 1); return s; }
-  static constexpr int PRE = prefix();
-};
-template <int S> struct CarStage {
-  static constexpr int per_control() { int s = 0; for (int j = 0; j < S - 1; ++j) s += kTileSamples * ((S - 1 - j) | 1); return s; }
-  static constexpr int PER_C = per_control();
-  static constexpr int UB = 2 * PER_C;                 // upper-bound rows: 16 x (S|1)
-  static constexpr int SIZE = UB + kTileSamples * (S | 1);
 };
 
 template <typename T, int S> struct CarArgs {
@@ -135,33 +126,166 @@ __device__ void car_final_rows(const CarArgs<T, S> &A, const CarEgo<T, S> &E, in
   }
 }
 
-template <typename T, int S, int WARPS> struct CarSmem {
-  CarEgo<T, S> ego;
-  T stage[WARPS][CarStage<S>::SIZE];
-};
+
 
 // per-chain sensitivity state
 template <typename T> struct CarChain { T rx, ry, wx, wy; };
 
-// staging offsets of column j inside a control's block (folds to a constant after unrolling)
-template <int S> __device__ __forceinline__ constexpr int car_stride(int j) { return (S - 1 - j) | 1; }
-template <int S> __device__ __forceinline__ constexpr int car_pre(int j) {
-  int s = 0;
-  for (int jj = 0; jj < j; ++jj) s += kTileSamples * car_stride<S>(jj);
-  return s;
-}
+#ifndef SAA_CAR_WARPS
+#define SAA_CAR_WARPS 12   // warps per block (one block per SM; shared memory = WARPS x CarPass::SIZE)
+#endif
+#ifndef SAA_CAR_NPASS
+#define SAA_CAR_NPASS 4    // the S-1 chains of a control are processed in NPASS groups, see CarPass
+#endif
 
-template <typename T, int S, int J>
+// The chains (control steps j) of a tile are processed in NPASS passes over the horizon so that
+// only part of the tile's entries is staged at a time: with 4 passes staging drops from 51 KB to 16 KB per
+// warp, i.e. 12 instead of 4 resident warps per SM (1.72 -> 1.36 ms at M = 1e6); the price is that the (cheap) rollout and
+// geometry are recomputed in every pass.  Group boundaries balance the staged sizes.
+template <int S, int NPASS> struct CarPass {
+  __host__ __device__ static constexpr int bound(int p) {           // first chain of pass p
+    if (NPASS == 1) return p == 0 ? 0 : S - 1;
+    const int total = (S - 1) * S / 2;
+    int acc = 0, j = 0, q = 0;
+    while (q < p && j < S - 1) {
+      acc += S - 1 - j; ++j;
+      if (acc * NPASS >= total * (q + 1)) ++q;
+    }
+    return p >= NPASS ? S - 1 : j;
+  }
+  __host__ __device__ static constexpr int pre(int j0, int j) {     // staging offset of column j inside its pass
+    int s = 0;
+    for (int jj = j0; jj < j; ++jj) s += kTileSamples * ((S - 1 - jj) | 1);
+    return s;
+  }
+  __host__ __device__ static constexpr int per_control() {          // largest staged block of one control
+    int m = 0;
+    for (int p = 0; p < NPASS; ++p) { const int v = pre(bound(p), bound(p + 1)); m = v > m ? v : m; }
+    return m;
+  }
+  static constexpr int PER_C = per_control();
+  static constexpr int UB = 2 * PER_C;          // upper-bound rows: 16 x (S|1), first pass only
+  static constexpr int SIZE = UB + kTileSamples * (S | 1);
+};
+
+template <typename T, int S, int WARPS> struct CarSmem {
+  CarEgo<T, S> ego;
+  T stage[WARPS][CarPass<S, SAA_CAR_NPASS>::SIZE];
+};
+
+template <typename T, int S, int J0, int J, int J1>
 __device__ __forceinline__ void car_copy_cols(const CarArgs<T, S> &A, const T *stage, i64 sbase, int ns,
                                               int lane) {
-  if constexpr (J < S - 1) {
+  if constexpr (J < J1) {
     using C = CarCol<S, J>;
+    using Ps = CarPass<S, SAA_CAR_NPASS>;
     i64 sb = sbase, mout = A.M_out;
     opaque(sb); opaque(mout);   // 2 IMADs per column instead of 2(S-1) live 64-bit bases
-    copy_run<T, C::L, C::STRIDE>(A.Ax + (C::CA0 + mout * C::CB0 + sb * C::L), stage + C::PRE, ns * C::L, lane);
+    copy_run<T, C::L, C::STRIDE>(A.Ax + (C::CA0 + mout * C::CB0 + sb * C::L), stage + Ps::pre(J0, J),
+                                 ns * C::L, lane);
     copy_run<T, C::L, C::STRIDE>(A.Ax + (C::CA1 + mout * C::CB1 + sb * C::L),
-                                 stage + CarStage<S>::PER_C + C::PRE, ns * C::L, lane);
-    car_copy_cols<T, S, J + 1>(A, stage, sbase, ns, lane);
+                                 stage + Ps::PER_C + Ps::pre(J0, J), ns * C::L, lane);
+    car_copy_cols<T, S, J0, J + 1, J1>(A, stage, sbase, ns, lane);
+  }
+}
+
+// One pass over the horizon for the chains j in [J0, J1) of this lane's control c.
+// FIRST: also the upper bounds, Z_i (values that do not depend on the chain group).
+template <typename T, int S, int J0, int J1, bool FIRST>
+__device__ __forceinline__ void car_pass(const CarArgs<T, S> &A, const CarEgo<T, S> &E, T *stage, int c,
+                                         int si, T qx, T qy, T wx, T wy, T w_s, T w_r,
+                                         const T (&dwx)[S], const T (&dwy)[S], T &zmax_out) {
+  using Ps = CarPass<S, SAA_CAR_NPASS>;
+  constexpr int NJ = J1 - J0;
+  const T dt = A.dt, wsdt = w_s * dt;
+  T *cstage = stage + c * Ps::PER_C;
+  T *ubrow = stage + Ps::UB + si * (S | 1);
+  CarChain<T> ch[NJ > 0 ? NJ : 1];
+  CarChain<T> cu{T(0), T(0), T(0), T(0)};     // tangent along u itself (for grad g . u)
+  T zmax = -INFINITY;
+  static_for<0, S + 1>([&](auto kc) {
+    constexpr int k = decltype(kc)::value;
+    // geometry at state k (car/driving.py:150-154, :227-231)
+    const T dx = E.p[k][0] - qx, dy = E.p[k][1] - qy;
+    const T n2 = fma(dx, dx, dy * dy);
+    const T inv_n = rsqrt_t(n2);
+    const T nrm = n2 * inv_n;
+    const T nhx = dx * inv_n, nhy = dy * inv_n;
+    // chains of this pass that are alive at state k: J0 <= j <= min(k-2, J1-1)
+    constexpr int JE = (k - 1 < J1) ? (k - 1) : J1;          // exclusive end
+    if constexpr (k >= 1) {
+      // row k of the sample: d g_k / d u_{j,c} = -n_k . rho_k^{(j,c)}
+      static_for<J0, (JE > J0 ? JE : J0)>([&](auto jc) {
+        constexpr int j = decltype(jc)::value;
+        cstage[Ps::pre(J0, j) + si * CarCol<S, j>::STRIDE + (k - j - 2)] =
+            -fma(nhx, ch[j - J0].rx, nhy * ch[j - J0].ry);
+      });
+      if constexpr (FIRST) {
+        // upper bound -g_k + grad g_k . u (:278), grad g . u summed over both controls
+        T gu = -fma(nhx, cu.rx, nhy * cu.ry);
+        gu += __shfl_xor_sync(0xffffffffu, gu, 16);
+        const T g = A.d_min - nrm;
+        zmax = fmax(zmax, g);
+        if (c == (k & 1)) ubrow[k - 1] = gu - g;
+      }
+    }
+    if constexpr (k < S) {
+      // one Euler-Maruyama step and its linearisation
+      const T om_n = dt * w_r * inv_n;
+      const T g11 = -om_n * fma(-nhx, nhx, T(1)), g12 = om_n * nhx * nhy,
+              g22 = -om_n * fma(-nhy, nhy, T(1));             // dt * dF/dp_ego
+      const T ttx = E.tt[c][k][0], tty = E.tt[c][k][1];
+      static_for<J0, (JE > J0 ? JE : J0)>([&](auto jc) {
+        constexpr int j = decltype(jc)::value;
+        CarChain<T> &h = ch[j - J0];
+        const T sy = wsdt * h.wy;
+        const T nwx = fma(g11, h.rx, fma(g12, h.ry, h.wx - sy));
+        const T nwy = fma(g12, h.rx, fma(g22, h.ry, h.wy - sy));
+        h.rx = fma(-dt, h.wx, h.rx + ttx);
+        h.ry = fma(-dt, h.wy, h.ry + tty);
+        h.wx = nwx; h.wy = nwy;
+      });
+      // chain j = k-1 is born at this step: rho_{k+1} = T_c(k), w_{k+1} = 0
+      if constexpr (k >= 1 && k - 1 >= J0 && k - 1 < J1) {
+        ch[k - 1 - J0].rx = ttx; ch[k - 1 - J0].ry = tty; ch[k - 1 - J0].wx = T(0); ch[k - 1 - J0].wy = T(0);
+      }
+      if constexpr (FIRST) {
+        const T uc = E.ucum[c][k];
+        const T sy = wsdt * cu.wy;
+        const T nwx = fma(g11, cu.rx, fma(g12, cu.ry, cu.wx - sy));
+        const T nwy = fma(g12, cu.rx, fma(g22, cu.ry, cu.wy - sy));
+        cu.rx = fma(-dt, cu.wx, fma(uc, ttx, cu.rx));
+        cu.ry = fma(-dt, cu.wy, fma(uc, tty, cu.ry));
+        cu.wx = nwx; cu.wy = nwy;
+      }
+      const T sp = w_s * (A.v_des - wy);
+      const T fx = fma(-w_r, nhx, sp), fy = fma(-w_r, nhy, sp);
+      const T nqx = fma(dt, wx, qx), nqy = fma(dt, wy, qy);
+      wx = wx + dt * fx + A.noise_c * dwx[k];
+      wy = wy + dt * fy + A.noise_c * dwy[k];
+      qx = nqx; qy = nqy;
+    }
+  });
+  zmax_out = zmax;
+}
+
+template <typename T, int S, int P>
+__device__ __forceinline__ void car_passes(const CarArgs<T, S> &A, const CarEgo<T, S> &E, T *stage, int c,
+                                           int si, int lane, i64 s, i64 s0, int ns, bool active, T qx,
+                                           T qy, T wx, T wy, T w_s, T w_r, const T (&dwx)[S],
+                                           const T (&dwy)[S]) {
+  using Ps = CarPass<S, SAA_CAR_NPASS>;
+  if constexpr (P < SAA_CAR_NPASS) {
+    constexpr int J0 = Ps::bound(P), J1 = Ps::bound(P + 1);
+    T zmax;
+    car_pass<T, S, J0, J1, P == 0>(A, E, stage, c, si, qx, qy, wx, wy, w_s, w_r, dwx, dwy, zmax);
+    if (P == 0 && A.Z != nullptr && c == 0 && active) A.Z[s] = zmax - A.ztol;
+    __syncwarp();
+    if (P == 0 && A.ub != nullptr)
+      copy_run<T, S, (S | 1)>(A.ub + A.ub_off + s0 * S, stage + Ps::UB, ns * S, lane);
+    car_copy_cols<T, S, J0, J0, J1>(A, stage, s0 + A.first_out, ns, lane);
+    __syncwarp();
+    car_passes<T, S, P + 1>(A, E, stage, c, si, lane, s, s0, ns, active, qx, qy, wx, wy, w_s, w_r, dwx, dwy);
   }
 }
 
@@ -179,9 +303,6 @@ car_assemble_kernel(const __grid_constant__ CarArgs<T, S> A) {
   if (A.Ax == nullptr) return;              // relaxed iteration: only the final rows are needed
   const CarEgo<T, S> &E = sm.ego;
   T *stage = sm.stage[warp];
-  T *cstage = stage + c * CarStage<S>::PER_C;
-  T *ubrow = stage + CarStage<S>::UB + si * (S | 1);
-  const T dt = A.dt;
 
   const i64 ntiles = (A.M + kTileSamples - 1) / kTileSamples;
 #pragma unroll 1
@@ -196,76 +317,10 @@ car_assemble_kernel(const __grid_constant__ CarArgs<T, S> A) {
       dwx[k] = __ldcs(A.dw + (i64)(2 * k) * A.Mpad + s);
       dwy[k] = __ldcs(A.dw + (i64)(2 * k + 1) * A.Mpad + s);
     }
-    T qx = __ldcs(A.x0 + s), qy = __ldcs(A.x0 + A.Mpad + s);
-    T wx = __ldcs(A.x0 + 2 * A.Mpad + s), wy = __ldcs(A.x0 + 3 * A.Mpad + s);
+    const T qx = __ldcs(A.x0 + s), qy = __ldcs(A.x0 + A.Mpad + s);
+    const T wx = __ldcs(A.x0 + 2 * A.Mpad + s), wy = __ldcs(A.x0 + 3 * A.Mpad + s);
     const T w_s = __ldcs(A.om + s), w_r = __ldcs(A.om + A.Mpad + s);
-    const T wsdt = w_s * dt;
-
-    CarChain<T> ch[S - 1];
-    CarChain<T> cu{T(0), T(0), T(0), T(0)};   // tangent along u itself (for grad g . u)
-    T zmax = -INFINITY;
-
-    static_for<0, S + 1>([&](auto kc) {
-      constexpr int k = decltype(kc)::value;
-      // geometry at state k (car/driving.py:150-154, :227-231)
-      const T dx = E.p[k][0] - qx, dy = E.p[k][1] - qy;
-      const T n2 = fma(dx, dx, dy * dy);
-      const T inv_n = rsqrt_t(n2);
-      const T nrm = n2 * inv_n;
-      const T nhx = dx * inv_n, nhy = dy * inv_n;
-      if constexpr (k >= 1) {
-        // row k of the sample: d g_k / d u_{j,c} = -n_k . rho_k^{(j,c)}, live for j <= k-2
-        static_for<0, (k >= 2 ? k - 1 : 0)>([&](auto jc) {
-          constexpr int j = decltype(jc)::value;
-          cstage[CarCol<S, j>::PRE + si * CarCol<S, j>::STRIDE + (k - j - 2)] =
-              -fma(nhx, ch[j].rx, nhy * ch[j].ry);
-        });
-        // upper bound -g_k + grad g_k . u (:278), grad g . u summed over both controls
-        T gu = -fma(nhx, cu.rx, nhy * cu.ry);
-        gu += __shfl_xor_sync(0xffffffffu, gu, 16);
-        const T g = A.d_min - nrm;
-        zmax = fmax(zmax, g);
-        if (c == (k & 1)) ubrow[k - 1] = gu - g;
-      }
-      if constexpr (k < S) {
-        // one Euler-Maruyama step and its linearisation
-        const T om_n = dt * w_r * inv_n;
-        const T g11 = -om_n * fma(-nhx, nhx, T(1)), g12 = om_n * nhx * nhy,
-                g22 = -om_n * fma(-nhy, nhy, T(1));             // dt * dF/dp_ego
-        const T ttx = E.tt[c][k][0], tty = E.tt[c][k][1];
-        static_for<0, (k >= 2 ? k - 1 : 0)>([&](auto jc) {
-          constexpr int j = decltype(jc)::value;
-          const T sy = wsdt * ch[j].wy;
-          const T nwx = fma(g11, ch[j].rx, fma(g12, ch[j].ry, ch[j].wx - sy));
-          const T nwy = fma(g12, ch[j].rx, fma(g22, ch[j].ry, ch[j].wy - sy));
-          ch[j].rx = fma(-dt, ch[j].wx, ch[j].rx + ttx);
-          ch[j].ry = fma(-dt, ch[j].wy, ch[j].ry + tty);
-          ch[j].wx = nwx; ch[j].wy = nwy;
-        });
-        // chain j = k-1 is born at this step: rho_{k+1} = T_c(k), w_{k+1} = 0
-        if constexpr (k >= 1) { ch[k - 1].rx = ttx; ch[k - 1].ry = tty; ch[k - 1].wx = T(0); ch[k - 1].wy = T(0); }
-        {
-          const T uc = E.ucum[c][k];
-          const T sy = wsdt * cu.wy;
-          const T nwx = fma(g11, cu.rx, fma(g12, cu.ry, cu.wx - sy));
-          const T nwy = fma(g12, cu.rx, fma(g22, cu.ry, cu.wy - sy));
-          cu.rx = fma(-dt, cu.wx, fma(uc, ttx, cu.rx));
-          cu.ry = fma(-dt, cu.wy, fma(uc, tty, cu.ry));
-          cu.wx = nwx; cu.wy = nwy;
-        }
-        const T sp = w_s * (A.v_des - wy);
-        const T fx = fma(-w_r, nhx, sp), fy = fma(-w_r, nhy, sp);
-        const T nqx = fma(dt, wx, qx), nqy = fma(dt, wy, qy);
-        wx = wx + dt * fx + A.noise_c * dwx[k];
-        wy = wy + dt * fy + A.noise_c * dwy[k];
-        qx = nqx; qy = nqy;
-      }
-    });
-    if (A.Z != nullptr && c == 0 && active) A.Z[s] = zmax - A.ztol;
-    __syncwarp();
-    if (A.ub != nullptr) copy_run<T, S, (S | 1)>(A.ub + A.ub_off + s0 * S, stage + CarStage<S>::UB, ns * S, lane);
-    car_copy_cols<T, S, 0>(A, stage, s0 + A.first_out, ns, lane);
-    __syncwarp();
+    car_passes<T, S, 0>(A, E, stage, c, si, lane, s, s0, ns, active, qx, qy, wx, wy, w_s, w_r, dwx, dwy);
   }
 }
 
