@@ -39,6 +39,12 @@
 #ifndef SAA_BPS
 #define SAA_BPS 2          // resident blocks per SM the kernel is compiled for
 #endif
+#ifndef SAA_GX
+#define SAA_GX 0           // 1: lanes exchange (p, tangent) once per step; 0: partial sums per (step, obstacle)
+#endif
+#ifndef SAA_Z_INLINE
+#define SAA_Z_INLINE 0     // 1: z-axis mean rows inside the assemble kernel (measured 9 % slower)
+#endif
 
 namespace saa {
 
@@ -331,6 +337,7 @@ drone_assemble_kernel(const __grid_constant__ DroneArgs<T, S> A) {
     const T c2 = T(2) * A.drag;
 
     // ---------------- z axis: feeds only the sample-mean rows -----------------
+#if SAA_Z_INLINE    // z-axis mean rows inside the assemble kernel (default: drone_zmean_kernel)
     {
       T a22z[S];
       T p = A.x0[2], v = A.x0[5], tp = T(0), tv = T(0);
@@ -365,6 +372,7 @@ drone_assemble_kernel(const __grid_constant__ DroneArgs<T, S> A) {
         lp = nlp; lv = nlv;
       }
     }
+#endif
 
     // ---------------- own axis (x or y): rollout + constraint values ----------
     T P[S + 1], A22[S];
@@ -378,6 +386,14 @@ drone_assemble_kernel(const __grid_constant__ DroneArgs<T, S> A) {
       T p = a ? A.x0[1] : A.x0[0], v = a ? A.x0[4] : A.x0[3], tp = T(0), tv = T(0);
       T zmax = -INFINITY;
       P[0] = p;
+#if SAA_GX == 1
+      T qo[3], oco[3];                                   // the partner axis' obstacle data
+#pragma unroll
+      for (int o = 0; o < 3; ++o) {
+        qo[o] = __shfl_xor_sync(0xffffffffu, q[o], 16);
+        oco[o] = a ? A.oc[o][0] : A.oc[o][1];
+      }
+#endif
 #if SAA_COPY >= 3
       using StU = Stager<T, 3 * S>;
       const i64 gu = ub_off + s0 * (3 * S);
@@ -402,13 +418,25 @@ drone_assemble_kernel(const __grid_constant__ DroneArgs<T, S> A) {
         v = v + dt * acc + nz * (SAA_PRELOAD ? dwa[k] : dwa_p[(i64)k * 3 * A.Mpad]);
         p = np_; tp = ntp; tv = ntv;
         P[k + 1] = p;
+#if SAA_GX == 1
+        // one exchange of (p, tangent) per step instead of two per (step, obstacle)
+        const T po = __shfl_xor_sync(0xffffffffu, p, 16), tpo = __shfl_xor_sync(0xffffffffu, tp, 16);
+#endif
 #pragma unroll
         for (int o = 0; o < 3; ++o) {
           const T d = p - oca[o];
           const T w = q[o] * d * d;                       // own-axis part of 1 - g
           const T e = fma(T(-2) * q[o] * d, tp, w);       // own-axis part of 1 - g + grad g . u
+#if SAA_GX == 1
+          const T d2 = po - oco[o];
+          const T w2 = qo[o] * d2 * d2;
+          const T e2 = fma(T(-2) * qo[o] * d2, tpo, w2);
+          const T wsum = a ? w2 + w : w + w2;             // x part + y part in both lanes (same rounding)
+          const T esum = a ? e2 + e : e + e2;
+#else
           const T wsum = w + __shfl_xor_sync(0xffffffffu, w, 16);
           const T esum = e + __shfl_xor_sync(0xffffffffu, e, 16);
+#endif
           zmax = fmax(zmax, T(1) - wsum);
           if (a == (k & 1))                               // the two lanes of a sample share the stores
             ubrow[o * S + k] = fma(esum - T(1), A.ubscale, -A.ubpad);
@@ -450,6 +478,78 @@ drone_assemble_kernel(const __grid_constant__ DroneArgs<T, S> A) {
 #pragma unroll
     for (int w = 0; w < WARPS; ++w) acc += sm.wacc[w][r];
     A.partials[(i64)blockIdx.x * Rd::N + r] = acc;
+  }
+}
+
+// ---- z-axis rows of the sample mean (separate, tiny kernel) ---------------------------
+// The z axis never enters the planar obstacle rows; it only contributes d x_S^z / d u^z and the
+// z linearisation offsets to the sample-mean rows.  One thread per sample: rollout, then one
+// adjoint sweep carrying e_p and e_v; the 2S+1 sums stay in registers over the thread's samples
+// and are reduced once at the end.  Reads 8 + 8S bytes per sample.
+template <typename T, int S, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+drone_zmean_kernel(const __grid_constant__ DroneArgs<T, S> A, double *__restrict__ partials) {
+  using Rd = DroneRed<S>;
+  __shared__ double red[WARPS][2 * S + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double accp[S - 1], accv[S], valp = 0.0, valv = 0.0;
+#pragma unroll
+  for (int j = 0; j < S - 1; ++j) accp[j] = 0.0;
+#pragma unroll
+  for (int j = 0; j < S; ++j) accv[j] = 0.0;
+  const T dt = A.dt, c2 = T(2) * A.drag;
+  for (i64 s = (i64)blockIdx.x * blockDim.x + threadIdx.x; s < A.M; s += (i64)gridDim.x * blockDim.x) {
+    T dwz[S];
+#pragma unroll
+    for (int k = 0; k < S; ++k) dwz[k] = __ldcs(A.dw + (i64)(k * 3 + 2) * A.Mpad + s);
+    const T inv_m = T(1) / __ldcs(A.mass + s);
+    const T dtm = dt * inv_m, a21 = -A.kp * dtm, nz = A.noise_c * inv_m;
+    T a22z[S];
+    T p = A.x0[2], v = A.x0[5], tp = T(0), tv = T(0);
+#pragma unroll
+    for (int k = 0; k < S; ++k) {
+      const T absv = fabs(v);
+      const T a22 = T(1) - dtm * (A.kd + c2 * absv);
+      a22z[k] = a22;
+      const T u = A.us[k * 3 + 2];
+      const T acc = (u - A.kp * p - A.kd * v - A.drag * absv * v) * inv_m;
+      const T ntp = fma(dt, tv, tp);
+      const T ntv = fma(a22, tv, fma(a21, tp, dtm * u));
+      const T np_ = fma(dt, v, p);
+      v = v + dt * acc + nz * dwz[k];
+      p = np_; tp = ntp; tv = ntv;
+    }
+    valp += (double)(-(p - A.xf[2]) + tp);      // linearisation offsets (:271)
+    valv += (double)(-(v - A.xf[5]) + tv);
+    T pp = T(1), pv = T(0), vp = T(0), vv = T(1);   // adjoints of p_S (pp, pv) and v_S (vp, vv)
+#pragma unroll
+    for (int j = S - 1; j >= 0; --j) {
+      if (j < S - 1) accp[j] += (double)(pv * dtm);
+      accv[j] += (double)(vv * dtm);
+      const T npp = fma(a21, pv, pp), npv = fma(a22z[j], pv, dt * pp);
+      const T nvp = fma(a21, vv, vp), nvv = fma(a22z[j], vv, dt * vp);
+      pp = npp; pv = npv; vp = nvp; vv = nvv;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < S - 1; ++j) { const double r = sum32(accp[j]); if (lane == 0) red[warp][j] = r; }
+#pragma unroll
+  for (int j = 0; j < S; ++j) { const double r = sum32(accv[j]); if (lane == 0) red[warp][S - 1 + j] = r; }
+  { const double r = sum32(valp); if (lane == 0) red[warp][2 * S - 1] = r; }
+  { const double r = sum32(valv); if (lane == 0) red[warp][2 * S] = r; }
+  __syncthreads();
+  // one full row of partials per block: zeros except the z slots
+  double *row = partials + (i64)blockIdx.x * Rd::N;
+  for (int r = threadIdx.x; r < Rd::N; r += WARPS * 32) {
+    int src = -1;
+    if (r >= Rd::FIN_P + 2 * (S - 1) && r < Rd::FIN_P + 3 * (S - 1)) src = r - (Rd::FIN_P + 2 * (S - 1));
+    else if (r >= Rd::FIN_V + 2 * S && r < Rd::FIN_V + 3 * S) src = S - 1 + r - (Rd::FIN_V + 2 * S);
+    else if (r == Rd::VAL + 2) src = 2 * S - 1;
+    else if (r == Rd::VAL + 5) src = 2 * S;
+    double acc = 0.0;
+    if (src >= 0)
+      for (int w = 0; w < WARPS; ++w) acc += red[w][src];
+    row[r] = acc;
   }
 }
 

@@ -287,15 +287,24 @@ int launch_drone_assemble(saa_handle *h, const double *us, int scp_iter, void *A
   A.Z = (T *)Z;
   const i64 ntiles = (h->M_local + kTileSamples - 1) / kTileSamples;
   const int grid = grid_for(h, ntiles, kWarps, kBlocksPerSM);
-  int rc = ensure_scratch(h, (i64)grid * DroneRed<kS>::N);
+  // rows [0, grid) of the partial sums come from the assemble kernel, rows [grid, grid + gridz)
+  // from the z-axis kernel
+  constexpr int kZWarps = 4;
+  const int gridz = SAA_Z_INLINE ? 0
+      : (int)std::max<i64>(1, std::min<i64>((h->M_local + kZWarps * 32 - 1) / (kZWarps * 32), (i64)h->n_sms * 2));
+  int rc = ensure_scratch(h, (i64)(grid + gridz) * DroneRed<kS>::N);
   if (rc) return rc;
   A.partials = h->d_partials;
   auto kern = drone_assemble_kernel<T, kS, kWarps>;
   SAA_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
   kern<<<grid, kWarps * 32, sizeof(Smem), st>>>(A);
   SAA_CUDA(h, cudaGetLastError());
+  if (gridz > 0) {
+    drone_zmean_kernel<T, kS, kZWarps><<<gridz, kZWarps * 32, 0, st>>>(A, h->d_partials + (i64)grid * DroneRed<kS>::N);
+    SAA_CUDA(h, cudaGetLastError());
+  }
   const int n = DroneRed<kS>::N;
-  reduce_partials_kernel<double><<<(n + 3) / 4, 128, 0, st>>>(h->d_partials, grid, n, sums);
+  reduce_partials_kernel<double><<<(n + 3) / 4, 128, 0, st>>>(h->d_partials, grid + gridz, n, sums);
   SAA_CUDA(h, cudaGetLastError());
   return SAA_OK;
 }
