@@ -49,6 +49,11 @@ class OSQPLike:
         self.q = np.asarray(q, dtype=np.float64).copy()
         self.l = np.maximum(np.asarray(l, dtype=np.float64), -_INF)
         self.u = np.minimum(np.asarray(u, dtype=np.float64), _INF)
+        if polish:
+            # OSQP's polishing step returns a high-accuracy solution of the active-set KKT system;
+            # this stand-in emulates it by iterating to 1e-6 (the SCP of the reference does not
+            # converge when its QPs are only solved to 3e-4, see examples/car_scp.py)
+            eps_abs, eps_rel, max_iter = min(eps_abs, 1e-6), min(eps_rel, 1e-6), max(max_iter, 200000)
         self.opts = SimpleNamespace(eps_abs=eps_abs, eps_rel=eps_rel, max_iter=max_iter, rho=rho,
                                     sigma=sigma, alpha=alpha, warm_start=warm_start, verbose=verbose,
                                     scaling=scaling, adaptive_rho_interval=adaptive_rho_interval,
