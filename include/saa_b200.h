@@ -185,6 +185,24 @@ int saa_merge_shard(saa_handle *h, const void *shard_Ax_dev, const void *shard_u
                     int64_t M_shard, int64_t first, void *Ax_dev, void *u_dev, void *stream);
 
 /*
+ * Multi-GPU gather, factored variant (drone).  What crosses NVLink is not the 1140 Jacobian
+ * entries of a sample but the two factors they are products of: the 380 control
+ * sensitivities d p_k / d u_{j,a} and the 46-value trajectory record (p_1..p_S and the scaled
+ * obstacle matrices per axis) -- 3.4 KB instead of 9.1 KB per sample.  A rank calls
+ * saa_linearize_factored with (peer-mapped) fsp / fp / u pointers of the matrix owner, laid out
+ * for the M_out samples of the output geometry (saa_factored_sizes elements); after a barrier
+ * the owner calls saa_expand_factored for the sample range of the other ranks, which forms the
+ * same products with the same instructions as saa_linearize_assemble (bitwise identical values).
+ * The upper bounds, Z and the mean sums are produced by saa_linearize_factored as usual.
+ */
+int saa_factored_sizes(const saa_handle *h, int64_t *n_sp, int64_t *n_p);
+int saa_linearize_factored(saa_handle *h, const double *us_host, int scp_iter, void *fsp_dev,
+                           void *fp_dev, void *u_dev, void *Z_dev, double *mean_sums_dev,
+                           void *stream);
+int saa_expand_factored(saa_handle *h, int scp_iter, const void *fsp_dev, const void *fp_dev,
+                        int64_t sample_begin, int64_t sample_count, void *Ax_dev, void *stream);
+
+/*
  * Peer-mapped buffers for the fused multi-GPU gather (one process per GPU).  The
  * owner allocates with saa_shared_alloc (plain cudaMalloc on `device`) and sends the
  * 64-byte handle to the other processes (any host channel, e.g. torch.distributed);

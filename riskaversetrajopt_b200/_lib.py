@@ -65,6 +65,11 @@ _PROTOTYPES = {
                                      C.c_void_p]),
     "saa_merge_shard": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
                                   C.c_void_p, C.c_void_p]),
+    "saa_factored_sizes": (C.c_int, [_H, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "saa_linearize_factored": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.c_void_p]),
+    "saa_expand_factored": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
+                                      C.c_void_p, C.c_void_p]),
     "saa_shared_alloc": (C.c_int, [C.c_int, C.c_int64, C.POINTER(C.c_void_p), C.c_char_p]),
     "saa_shared_open": (C.c_int, [C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]),
     "saa_shared_close": (C.c_int, [C.c_int, C.c_void_p]),

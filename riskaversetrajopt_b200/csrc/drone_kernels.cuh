@@ -13,40 +13,38 @@
 //   a22_k = 1 - dt (kd + 2c|v_k|)/m,   d v+/du = dt/m.
 //
 // Thread mapping: one warp owns a tile of 16 samples; lanes 0-15 run the x axis
-// of those samples, lanes 16-31 the y axis (the z axis, which only feeds the
-// sample-mean rows, is split between the two lanes of a sample by an adjoint
-// pass).  For each control step j the lane runs the sensitivity chain
-// k = j+1..S in registers and stages the 3*(S-1-j) CSC entries of its sample
-// for column (j, axis) in shared memory; the warp then streams the two column
-// sub-runs (16 samples x 3*(S-1-j) contiguous doubles each) to global memory
-// with consecutive lanes on consecutive addresses.
+// of those samples, lanes 16-31 the y axis (the z axis only feeds the sample-mean
+// rows: drone_zmean_kernel).  For each control step j the lane runs the
+// sensitivity chain k = j+1..S in registers and stages the 3*(S-1-j) CSC entries
+// of its sample for column (j, axis) in shared memory; the warp then streams the
+// two column sub-runs (16 samples x 3*(S-1-j) contiguous doubles each) to global
+// memory, consecutive lanes on consecutive 16-byte chunks.
+//
+// Three modes of the same kernel:
+//   FULL    rollout -> chains -> CSC entries                       (single GPU, or a rank's own block)
+//   FACTOR  rollout -> chains -> FACTORED record of the block: the sensitivities d p_k/d u_j
+//           (190 per sample and axis) and the trajectory (p_1..p_S, -2 escale Q: 23 per sample
+//           and axis) instead of their 570 products -- 3.4 KB instead of 9.1 KB per sample,
+//           which is what has to cross NVLink in the multi-GPU gather
+//   EXPAND  factored record -> CSC entries (run by the rank that owns the matrix); the
+//           products are formed by the same instructions as in FULL, so the result is bitwise
+//           identical to a single-GPU run
 #pragma once
 #include "saa_common.cuh"
 
-// ---- tuning switches (defaults = the measured best; see profiles/ and DESIGN.md) ----
-#ifndef SAA_PRELOAD
-#define SAA_PRELOAD 1      // load the tile's noise increments before the rollouts
-#endif
-#ifndef SAA_PREFETCH
-#define SAA_PREFETCH 0     // prefetch.global.L2 of the next tile's input lines
-#endif
-#ifndef SAA_PAIR
-#define SAA_PAIR 0         // process chains (J, S-2-J) together
-#endif
+// ---- tuning switches (defaults = the measured best; history in profiles/README.md) ----
 #ifndef SAA_COPY
-#define SAA_COPY 4         // 0: 8-byte loop, 1: 8-deep batches, 2: non-inlined body, 3: TMA bulk stores, 4: 16-byte vector copy
+#define SAA_COPY 4         // 4: 16-byte shared loads -> 16-byte streaming stores; 3: TMA bulk stores
+                           // (cp.async.bulk, correct but measured 2-3x slower on these short,
+                           // 16-byte-aligned runs)
 #endif
 #ifndef SAA_BPS
 #define SAA_BPS 2          // resident blocks per SM the kernel is compiled for
 #endif
-#ifndef SAA_GX
-#define SAA_GX 0           // 1: lanes exchange (p, tangent) once per step; 0: partial sums per (step, obstacle)
-#endif
-#ifndef SAA_Z_INLINE
-#define SAA_Z_INLINE 0     // 1: z-axis mean rows inside the assemble kernel (measured 9 % slower)
-#endif
 
 namespace saa {
+
+enum { DRONE_FULL = 0, DRONE_FACTOR = 1, DRONE_EXPAND = 2 };
 
 template <int S> struct DroneRed {
   static constexpr int FIN_P = 0;                 // + a*(S-1) + j   (a<3, j<S-1)
@@ -54,6 +52,9 @@ template <int S> struct DroneRed {
   static constexpr int VAL = FIN_V + 3 * S;       // + r             (r<6)
   static constexpr int N = VAL + 6;
 };
+
+// rows of the factored trajectory record per (axis): p_1..p_S, then the 3 scaled Q entries
+template <int S> struct DroneFac { static constexpr int ROWS = S + 3; };
 
 template <typename T, int S> struct DroneArgs {
   const T *mass, *dw, *q;   // packed: mass[M]; dw[(k*3+a)*Mpad+s]; q[(o*2+a)*Mpad+s]
@@ -73,44 +74,27 @@ template <typename T, int S> struct DroneArgs {
   i64 ub_off;               // row of local sample 0's first sample row
   T *Z;                     // per-sample max constraint (nullptr: skip)
   double *partials;         // [gridDim.x][DroneRed<S>::N]
+  // factored record (FACTOR writes, EXPAND reads), laid out for M_out samples:
+  //   fsp[M_out * FB(j,a) + sample * (S-1-j) + kk] = d p_{j+2+kk} / d u_{j,a}
+  //   fp[(a * (S+3) + r) * M_out + sample]         = p_{r+1} (r < S) | -2 escale Q_o,aa (r = S+o)
+  T *fsp, *fp;
+  i64 s_begin;              // EXPAND: first sample (of the M_out geometry) to expand; M = count
 };
 
-// ---- sensitivity chains ----------------------------------------------------------
+// ---- column geometry --------------------------------------------------------------------
 // Column (J, axis) of a sample holds rows k = J+2..S for each of the 3 obstacles:
-// LEN = 3 (S-1-J) contiguous values.  Chains are processed in pairs (J, S-2-J) so
-// that every pass has the same amount of work (LEN1 + LEN2 = 3S) and two
-// independent dependency chains per thread (ILP).
+// LEN = 3 (S-1-J) contiguous values.
 template <int S, int J> struct DroneChain {
   static constexpr int L = S - 1 - J;      // rows k = J+2..S carry an entry
   static constexpr int LEN = 3 * L;        // per-sample run length in the CSC column
-  static constexpr int STRIDE = LEN | 1;   // odd stride: conflict-free 64-bit staging stores
   // CSC position of sample 0's run of column c = 3J + a in a matrix with M samples is
   // CAa + M * CBa: every earlier control step holds 6 final-row + 3 control-row
   // entries and 2 columns of 3(S-1-j') values per sample (layout.cuh, Layout::build)
   static constexpr i64 CA0 = 9 * J + 2, CA1 = CA0 + 3;
   static constexpr i64 CB0 = 6 * J * (S - 1) - 3 * J * (J - 1), CB1 = CB0 + 3 * (S - 1 - J);
+  // factored record: column (J, a) starts at M * FBa, L values per sample
+  static constexpr i64 FB0 = 2 * J * (S - 1) - J * (J - 1), FB1 = FB0 + L;
 };
-
-template <typename T, int S> struct DroneChainState {
-  T sp, sv;
-};
-
-// one step k -> k+1 of chain J, staging the three entries of row k+1
-template <typename T, int S, int J>
-__device__ __forceinline__ void drone_chain_step(int k, const T (&P)[S + 1], const T (&A22)[S],
-                                                 const T (&q2)[3], const T (&oc)[3], T dt, T a21,
-                                                 T *mine, DroneChainState<T, S> &c) {
-  using C = DroneChain<S, J>;
-  const T nsp = fma(dt, c.sv, c.sp);
-  const T nsv = fma(A22[k], c.sv, a21 * c.sp);
-  c.sp = nsp; c.sv = nsv;                  // now d(p,v)_{k+1} / du_J
-  const int kk = k - J - 1;
-#pragma unroll
-  for (int o = 0; o < 3; ++o) {
-    const T coef = fma(q2[o], P[k + 1], oc[o]);    // escale * d g[o,k+1]/dp = q2 (p - c): oc holds -q2*c
-    mine[o * C::L + kk] = coef * c.sp;
-  }
-}
 
 template <typename T, int S, int WARPS>
 struct DroneSmem {
@@ -125,82 +109,48 @@ struct DroneSmem {
   double wacc[WARPS][DroneRed<S>::N];
 };
 
-// Copy n = ns*LEN staged values (row stride LEN + EXTRA) to a contiguous global run.
-template <typename T>
-__device__ __noinline__ void copy_run_rt(T *__restrict__ dst, const T *__restrict__ src, int n,
-                                         int extra, unsigned magic) {
-  const int lane = threadIdx.x & 31;
-#pragma unroll 1
-  for (int e0 = lane; e0 < n; e0 += 256) {
-    T v[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int e = min(e0 + u * 32, n - 1);
-      v[u] = src[e + (int)__umulhi((unsigned)e, magic) * extra];
-    }
-#pragma unroll
-    for (int u = 0; u < 8; ++u)
-      if (e0 + u * 32 < n) st_stream(dst + e0 + u * 32, v[u]);
-  }
-}
-template <typename T, int LEN, int EXTRA>
-__device__ __forceinline__ void copy_run8(T *__restrict__ dst, const T *__restrict__ src, int n,
-                                          int lane) {
-  constexpr unsigned MAGIC = (unsigned)((0x100000000ull + LEN - 1) / LEN);
-#if SAA_COPY == 2
-  copy_run_rt<T>(dst, src, n, EXTRA, MAGIC);
-#elif SAA_COPY == 1
-#pragma unroll 1
-  for (int e0 = lane; e0 < n; e0 += 256) {
-    T v[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int e = min(e0 + u * 32, n - 1);
-      const int i = EXTRA ? (int)__umulhi((unsigned)e, MAGIC) : 0;
-      v[u] = src[e + i * EXTRA];
-    }
-#pragma unroll
-    for (int u = 0; u < 8; ++u)
-      if (e0 + u * 32 < n) st_stream(dst + e0 + u * 32, v[u]);
-  }
-#else
-  copy_run<T, LEN, LEN + EXTRA>(dst, src, n, lane);
-#endif
-}
-
 // Launch constants the copy-out needs, read from the parameter bank ONCE and pinned in
 // registers (an LDC in front of every column store showed up as long-scoreboard stalls).
 template <typename T> struct DroneOut {
-  T *Ax;
+  T *Ax, *fsp;
   i64 mout, first;
 };
 
-template <typename T, int S, int J>
-__device__ __forceinline__ void drone_chain_pairs(const DroneArgs<T, S> &A, const DroneOut<T> &O,
-                                                  const T (&P)[S + 1],
-                                                  const T (&A22)[S], const T (&q2)[3],
-                                                  const T (&oca)[3], T a21, T dtm, T *stage,
-                                                  double *wacc, int a, int si, int lane, i64 s0,
-                                                  int ns, bool active) {
+// stage -> global for one column pair
+template <typename T, int LEN>
+__device__ __forceinline__ void drone_flush(T *base, T *stg, i64 g0x, i64 g0y, int a, int si, int ns,
+                                            int lane) {
+  using St = Stager<T, LEN>;
+#if SAA_COPY == 3
+  fence_async_smem();
+  __syncwarp();
+  St::flush(base, stg, a, si, a ? g0y : g0x, ns);
+#else
+  __syncwarp();
+  St::copy_vec(base, stg, 0, g0x, ns, lane);
+  St::copy_vec(base, stg, 1, g0y, ns, lane);
+  __syncwarp();
+#endif
+}
+
+// ---- sensitivity chains, one CSC column pair (x and y column of control step J) per pass ----
+template <typename T, int S, int J, int MODE>
+__device__ __forceinline__ void drone_chains(const DroneArgs<T, S> &A, const DroneOut<T> &O,
+                                             const T (&P)[S + 1], const T (&A22)[S],
+                                             const T (&q2)[3], const T (&oca)[3], T a21, T dtm,
+                                             T *stage, double *wacc, int a, int si, int lane, i64 s0,
+                                             int ns, bool active) {
   using Rd = DroneRed<S>;
-  constexpr int J2 = SAA_PAIR ? S - 2 - J : J;            // partner chain (J2 >= J)
-  if constexpr (SAA_PAIR ? (J > J2) : (J >= S - 1)) {
-    // all chains with sample rows are done; last control step J = S-1 has none:
-    // only d v_S/du = dt/m enters the mean rows
-    const double rv = sum16((double)(active ? dtm : T(0)));
-    if (si == 0) wacc[Rd::FIN_V + a * S + (S - 1)] += rv;
+  if constexpr (J >= S - 1) {
+    // last control step: no sample rows, only d v_S/du = dt/m enters the mean rows
+    if constexpr (MODE != DRONE_EXPAND) {
+      const double rv = sum16((double)(active ? dtm : T(0)));
+      if (si == 0) wacc[Rd::FIN_V + a * S + (S - 1)] += rv;
+    }
   } else {
-    using C1 = DroneChain<S, J>;
-    using C2 = DroneChain<S, J2>;
-    constexpr bool PAIR = (J2 != J);
-    // optimisation barriers: keep per-chain coefficient math from being hoisted
-    // (common subexpressions across the unrolled chains would cost ~60 live doubles)
-    T q2j[3] = {q2[0], q2[1], q2[2]}, ocj[3] = {-q2[0] * oca[0], -q2[1] * oca[1], -q2[2] * oca[2]};
-    opaque(q2j[0]); opaque(q2j[1]); opaque(q2j[2]);
-    opaque(ocj[0]); opaque(ocj[1]); opaque(ocj[2]);
-#if SAA_COPY >= 3
-    static_assert(!SAA_PAIR, "TMA / vector copy-out is implemented for single chains");
-    using St = Stager<T, C1::LEN>;
+    using C = DroneChain<S, J>;
+    constexpr int SLEN = (MODE == DRONE_FACTOR) ? C::L : C::LEN;   // staged values per sample
+    using St = Stager<T, SLEN>;
     static_assert(St::SIZE <= DroneSmem<T, S, 1>::HALF, "staging buffer too small");
 #if SAA_COPY == 3
     // upper bounds went through buffer 0, chain 0 takes buffer 1, chain 1 buffer 0, ...
@@ -208,83 +158,62 @@ __device__ __forceinline__ void drone_chain_pairs(const DroneArgs<T, S> &A, cons
 #else
     T *const stg = stage;
 #endif
-#ifdef SAA_ABL_SAMEADDR
-    i64 sbase = (s0 & 0xfff) + O.first, mout = O.mout;   // ablation (timing only): all tiles hit an L2-resident window
-#else
+    // optimisation barriers: keep per-chain coefficient math from being hoisted (common
+    // subexpressions across the unrolled chains would cost ~60 live doubles), and recompute the
+    // column bases per chain (2 IMADs) instead of keeping 2(S-1) of them live
+    T q2j[3] = {q2[0], q2[1], q2[2]}, ocj[3] = {-q2[0] * oca[0], -q2[1] * oca[1], -q2[2] * oca[2]};
+    opaque(q2j[0]); opaque(q2j[1]); opaque(q2j[2]);
+    opaque(ocj[0]); opaque(ocj[1]); opaque(ocj[2]);
     i64 sbase = s0 + O.first, mout = O.mout;
-#endif
-    opaque(sbase); opaque(mout);   // recompute the column bases per chain (2 IMADs) instead of keeping 2(S-1) of them live
-    const i64 g0 = (a ? C1::CA1 + mout * C1::CB1 : C1::CA0 + mout * C1::CB0) + sbase * C1::LEN;
-    T *mine1 = St::mine(stg, a, si, g0);
-    T *mine2 = mine1;
+    opaque(sbase); opaque(mout);
+    const i64 f0x = mout * C::FB0 + sbase * C::L, f0y = mout * C::FB1 + sbase * C::L;     // factored runs
+    const i64 g0x = C::CA0 + mout * C::CB0 + sbase * C::LEN, g0y = C::CA1 + mout * C::CB1 + sbase * C::LEN;
+    T *mine = St::mine(stg, a, si, MODE == DRONE_FACTOR ? (a ? f0y : f0x) : (a ? g0y : g0x));
 #if SAA_COPY == 3
     bulk_wait_read1();             // the column pair staged two steps ago has left this buffer
     __syncwarp();
 #endif
-#else
-    T *mine1 = stage + (a * kTileSamples + si) * C1::STRIDE;
-    T *mine2 = stage + 2 * kTileSamples * C1::STRIDE + (a * kTileSamples + si) * C2::STRIDE;
-#endif
-    DroneChainState<T, S> c1{T(0), dtm}, c2{T(0), dtm};   // d(p,v)_{J+1}/du_J = (0, dt/m)
+    T sp = T(0), sv = dtm;         // d(p,v)_{J+1}/du_J = (0, dt/m)
+    const T *fin = O.fsp + (a ? f0y : f0x) + (i64)(active ? si : 0) * C::L;   // EXPAND: this sample's chain
 #pragma unroll
     for (int k = J + 1; k < S; ++k) {
-#ifdef SAA_ABL_NOCHAIN
-      continue;   // ablation (timing only): no chain math, no staging stores
-#endif
-      drone_chain_step<T, S, J>(k, P, A22, q2j, ocj, A.dt, a21, mine1, c1);
-      if (PAIR && k >= J2 + 1) drone_chain_step<T, S, J2>(k, P, A22, q2j, ocj, A.dt, a21, mine2, c2);
+      const int kk = k - J - 1;
+      if constexpr (MODE == DRONE_EXPAND) {
+        sp = fin[kk];              // d p_{k+1}/du_J computed by the rank that owns the sample
+      } else {
+        const T nsp = fma(A.dt, sv, sp);
+        const T nsv = fma(A22[k], sv, a21 * sp);
+        sp = nsp; sv = nsv;        // now d(p,v)_{k+1} / du_J
+      }
+      if constexpr (MODE == DRONE_FACTOR) {
+        mine[kk] = sp;
+      } else {
+#pragma unroll
+        for (int o = 0; o < 3; ++o) {
+          const T coef = fma(q2j[o], P[k + 1], ocj[o]);   // escale * d g[o,k+1]/dp = q2 (p - c)
+          mine[o * C::L + kk] = coef * sp;
+        }
+      }
     }
-    // sample-mean rows: d p_S/du_J, d v_S/du_J summed over the tile
-    {
-      const double rp = sum16((double)(active ? c1.sp : T(0)));
-      const double rv = sum16((double)(active ? c1.sv : T(0)));
+    if constexpr (MODE != DRONE_EXPAND) {
+      // sample-mean rows: d p_S/du_J, d v_S/du_J summed over the tile
+      const double rp = sum16((double)(active ? sp : T(0)));
+      const double rv = sum16((double)(active ? sv : T(0)));
       if (si == 0) { wacc[Rd::FIN_P + a * (S - 1) + J] += rp; wacc[Rd::FIN_V + a * S + J] += rv; }
     }
-    if (PAIR) {
-      const double rp = sum16((double)(active ? c2.sp : T(0)));
-      const double rv = sum16((double)(active ? c2.sv : T(0)));
-      if (si == 0) { wacc[Rd::FIN_P + a * (S - 1) + J2] += rp; wacc[Rd::FIN_V + a * S + J2] += rv; }
-    }
-#if SAA_COPY == 3
-    fence_async_smem();
-    __syncwarp();
-    St::flush(O.Ax, stg, a, si, g0, ns);
-#elif SAA_COPY == 4
-    __syncwarp();
-    {
-      const i64 g0x = C1::CA0 + mout * C1::CB0 + sbase * C1::LEN;
-      const i64 g0y = C1::CA1 + mout * C1::CB1 + sbase * C1::LEN;
-      St::copy_vec(O.Ax, stg, 0, g0x, ns, lane);
-      St::copy_vec(O.Ax, stg, 1, g0y, ns, lane);
-    }
-    __syncwarp();
-#else
-    __syncwarp();
-    i64 sbase = s0 + O.first, mout = O.mout;
-    opaque(sbase); opaque(mout);   // recompute the column bases per chain (2 IMADs) instead of keeping 2(S-1) of them live
-    copy_run8<T, C1::LEN, C1::STRIDE - C1::LEN>(O.Ax + (C1::CA0 + mout * C1::CB0 + sbase * C1::LEN),
-                                                stage, ns * C1::LEN, lane);
-    copy_run8<T, C1::LEN, C1::STRIDE - C1::LEN>(O.Ax + (C1::CA1 + mout * C1::CB1 + sbase * C1::LEN),
-                                                stage + kTileSamples * C1::STRIDE, ns * C1::LEN, lane);
-    if (PAIR) {
-      const T *st2 = stage + 2 * kTileSamples * C1::STRIDE;
-      copy_run8<T, C2::LEN, C2::STRIDE - C2::LEN>(O.Ax + (C2::CA0 + mout * C2::CB0 + sbase * C2::LEN),
-                                                  st2, ns * C2::LEN, lane);
-      copy_run8<T, C2::LEN, C2::STRIDE - C2::LEN>(O.Ax + (C2::CA1 + mout * C2::CB1 + sbase * C2::LEN),
-                                                  st2 + kTileSamples * C2::STRIDE, ns * C2::LEN, lane);
-    }
-    __syncwarp();
-#endif
-    drone_chain_pairs<T, S, J + 1>(A, O, P, A22, q2, oca, a21, dtm, stage, wacc, a, si, lane, s0, ns,
-                                   active);
+    if constexpr (MODE == DRONE_FACTOR) drone_flush<T, SLEN>(O.fsp, stg, f0x, f0y, a, si, ns, lane);
+    else drone_flush<T, SLEN>(O.Ax, stg, g0x, g0y, a, si, ns, lane);
+    drone_chains<T, S, J + 1, MODE>(A, O, P, A22, q2, oca, a21, dtm, stage, wacc, a, si, lane, s0, ns,
+                                    active);
   }
 }
 
 // ---- K1: linearize + assemble ------------------------------------------------
-template <typename T, int S, int WARPS>
+template <typename T, int S, int WARPS, int MODE>
 __global__ void __launch_bounds__(WARPS * 32, SAA_BPS)
 drone_assemble_kernel(const __grid_constant__ DroneArgs<T, S> A) {
   using Rd = DroneRed<S>;
+  constexpr int FR = DroneFac<S>::ROWS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   auto &sm = *reinterpret_cast<DroneSmem<T, S, WARPS> *>(smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -294,12 +223,13 @@ drone_assemble_kernel(const __grid_constant__ DroneArgs<T, S> A) {
   for (int r = lane; r < Rd::N; r += 32) wacc[r] = 0.0;
   __syncwarp();
 
-  DroneOut<T> O{A.Ax, A.M_out, A.first_out};
+  DroneOut<T> O{A.Ax, A.fsp, A.M_out, A.first_out};
   {
-    i64 ax = (i64)O.Ax;
-    opaque(ax); opaque(O.mout); opaque(O.first);
-    O.Ax = (T *)ax;
+    i64 ax = (i64)O.Ax, fs = (i64)O.fsp;
+    opaque(ax); opaque(fs); opaque(O.mout); opaque(O.first);
+    O.Ax = (T *)ax; O.fsp = (T *)fs;
   }
+  if (MODE == DRONE_EXPAND) O.first = A.s_begin;
   i64 ub_base = (i64)A.ub, ub_off = A.ub_off;
   opaque(ub_base); opaque(ub_off);
   T *const ub_ptr = (T *)ub_base;
@@ -311,99 +241,49 @@ drone_assemble_kernel(const __grid_constant__ DroneArgs<T, S> A) {
     const int ns = (int)min((i64)kTileSamples, A.M - s0);
     const bool active = si < ns;
     const i64 s = s0 + (active ? si : 0);
-    // ---- all inputs of the tile in flight at once (one DRAM round trip) ----------
-    const T *dwz_p = A.dw + 2 * A.Mpad + s, *dwa_p = A.dw + a * A.Mpad + s;
-    T dwz[S], dwa[S];
-#pragma unroll
-    for (int k = 0; k < S; ++k) { if (SAA_PRELOAD) dwz[k] = __ldcs(dwz_p + (i64)k * 3 * A.Mpad); }
-#pragma unroll
-    for (int k = 0; k < S; ++k) { if (SAA_PRELOAD) dwa[k] = __ldcs(dwa_p + (i64)k * 3 * A.Mpad); }
-    T q[3];
-#pragma unroll
-    for (int o = 0; o < 3; ++o) q[o] = __ldcs(A.q + (o * 2 + a) * A.Mpad + s);
-    const T mass = __ldcs(A.mass + s);
-    // ... and the next tile's lines on their way into L2 (67 lines of 128 B per tile)
-    if (SAA_PREFETCH && tile + tstride < ntiles) {
-      const i64 sn = s0 + tstride * kTileSamples;
-      for (int r = lane; r < 3 * S + 7; r += 32) {
-        const T *pf = r < 3 * S ? A.dw + (i64)r * A.Mpad + sn
-                    : r < 3 * S + 6 ? A.q + (i64)(r - 3 * S) * A.Mpad + sn : A.mass + sn;
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
-      }
-    }
-    const T inv_m = T(1) / mass;
-    const T dt = A.dt, dtm = dt * inv_m, a21 = -A.kp * dtm;
-    const T nz = A.noise_c * inv_m;
-    const T c2 = T(2) * A.drag;
-
-    // ---------------- z axis: feeds only the sample-mean rows -----------------
-#if SAA_Z_INLINE    // z-axis mean rows inside the assemble kernel (default: drone_zmean_kernel)
-    {
-      T a22z[S];
-      T p = A.x0[2], v = A.x0[5], tp = T(0), tv = T(0);
-#pragma unroll
-      for (int k = 0; k < S; ++k) {
-        const T absv = fabs(v);
-        const T a22 = T(1) - dtm * (A.kd + c2 * absv);
-        a22z[k] = a22;
-        const T u = A.us[k * 3 + 2];
-        const T acc = (u - A.kp * p - A.kd * v - A.drag * absv * v) * inv_m;
-        const T ntp = fma(dt, tv, tp);
-        const T ntv = fma(a22, tv, fma(a21, tp, dtm * u));
-        const T np_ = fma(dt, v, p);
-        v = v + dt * acc + nz * (SAA_PRELOAD ? dwz[k] : dwz_p[(i64)k * 3 * A.Mpad]);
-        p = np_; tp = ntp; tv = ntv;
-      }
-      // linearisation offset of the final rows: -(x_S - x_f) + d x_S/du . u  (:271)
-      const T valz = (a == 0) ? (-(p - A.xf[2]) + tp) : (-(v - A.xf[5]) + tv);
-      const double rz = sum16((double)(active ? valz : T(0)));
-      if (si == 0) wacc[Rd::VAL + (a == 0 ? 2 : 5)] += rz;
-      // adjoint pass: lane a=0 carries e_p (row p_z), lane a=1 carries e_v (row v_z)
-      T lp = (a == 0) ? T(1) : T(0), lv = (a == 0) ? T(0) : T(1);
-#pragma unroll
-      for (int j = S - 1; j >= 0; --j) {
-        const double r = sum16((double)(active ? lv * dtm : T(0)));
-        if (si == 0) {
-          if (a == 1) wacc[Rd::FIN_V + 2 * S + j] += r;
-          else if (j < S - 1) wacc[Rd::FIN_P + 2 * (S - 1) + j] += r;
-        }
-        const T nlp = fma(a21, lv, lp);
-        const T nlv = fma(a22z[j], lv, dt * lp);
-        lp = nlp; lv = nlv;
-      }
-    }
-#endif
-
-    // ---------------- own axis (x or y): rollout + constraint values ----------
     T P[S + 1], A22[S];
     T q2[3], oca[3];
 #pragma unroll
-    for (int o = 0; o < 3; ++o) {
-      q2[o] = T(-2) * A.escale * q[o];
-      oca[o] = a ? A.oc[o][1] : A.oc[o][0];
-    }
-    {
+    for (int o = 0; o < 3; ++o) oca[o] = a ? A.oc[o][1] : A.oc[o][0];
+    T dtm = T(0), a21 = T(0);
+
+    if constexpr (MODE == DRONE_EXPAND) {
+      // the owner of the matrix re-creates the entries of another rank's samples from the record
+      const T *fp = A.fp + (i64)a * FR * O.mout + (O.first + s);
+#pragma unroll
+      for (int k = 1; k <= S; ++k) P[k] = __ldcs(fp + (i64)(k - 1) * O.mout);
+#pragma unroll
+      for (int o = 0; o < 3; ++o) q2[o] = __ldcs(fp + (i64)(S + o) * O.mout);
+      P[0] = T(0);
+#pragma unroll
+      for (int k = 0; k < S; ++k) A22[k] = T(0);
+    } else {
+      // ---- all inputs of the tile in flight at once (one DRAM round trip) ----------
+      const T *dwa_p = A.dw + a * A.Mpad + s;
+      T dwa[S];
+#pragma unroll
+      for (int k = 0; k < S; ++k) dwa[k] = __ldcs(dwa_p + (i64)k * 3 * A.Mpad);
+      T q[3];
+#pragma unroll
+      for (int o = 0; o < 3; ++o) q[o] = __ldcs(A.q + (o * 2 + a) * A.Mpad + s);
+      const T inv_m = T(1) / __ldcs(A.mass + s);
+      const T dt = A.dt;
+      dtm = dt * inv_m; a21 = -A.kp * dtm;
+      const T nz = A.noise_c * inv_m;
+      const T c2 = T(2) * A.drag;
+#pragma unroll
+      for (int o = 0; o < 3; ++o) q2[o] = T(-2) * A.escale * q[o];
+
+      // ---------------- own axis (x or y): rollout + constraint values ----------
       T p = a ? A.x0[1] : A.x0[0], v = a ? A.x0[4] : A.x0[3], tp = T(0), tv = T(0);
       T zmax = -INFINITY;
       P[0] = p;
-#if SAA_GX == 1
-      T qo[3], oco[3];                                   // the partner axis' obstacle data
-#pragma unroll
-      for (int o = 0; o < 3; ++o) {
-        qo[o] = __shfl_xor_sync(0xffffffffu, q[o], 16);
-        oco[o] = a ? A.oc[o][0] : A.oc[o][1];
-      }
-#endif
-#if SAA_COPY >= 3
       using StU = Stager<T, 3 * S>;
       const i64 gu = ub_off + s0 * (3 * S);
       T *ubrow = StU::mine(stage, 0, si, gu);
 #if SAA_COPY == 3
       bulk_wait_read1();           // buffer 0 was last used by the second-to-last column pair of the previous tile
       __syncwarp();
-#endif
-#else
-      T *ubrow = stage + si * (3 * S + 1);
 #endif
 #pragma unroll
       for (int k = 0; k < S; ++k) {
@@ -415,33 +295,22 @@ drone_assemble_kernel(const __grid_constant__ DroneArgs<T, S> A) {
         const T ntp = fma(dt, tv, tp);
         const T ntv = fma(a22, tv, fma(a21, tp, dtm * u));
         const T np_ = fma(dt, v, p);
-        v = v + dt * acc + nz * (SAA_PRELOAD ? dwa[k] : dwa_p[(i64)k * 3 * A.Mpad]);
+        v = v + dt * acc + nz * dwa[k];
         p = np_; tp = ntp; tv = ntv;
         P[k + 1] = p;
-#if SAA_GX == 1
-        // one exchange of (p, tangent) per step instead of two per (step, obstacle)
-        const T po = __shfl_xor_sync(0xffffffffu, p, 16), tpo = __shfl_xor_sync(0xffffffffu, tp, 16);
-#endif
 #pragma unroll
         for (int o = 0; o < 3; ++o) {
           const T d = p - oca[o];
           const T w = q[o] * d * d;                       // own-axis part of 1 - g
           const T e = fma(T(-2) * q[o] * d, tp, w);       // own-axis part of 1 - g + grad g . u
-#if SAA_GX == 1
-          const T d2 = po - oco[o];
-          const T w2 = qo[o] * d2 * d2;
-          const T e2 = fma(T(-2) * qo[o] * d2, tpo, w2);
-          const T wsum = a ? w2 + w : w + w2;             // x part + y part in both lanes (same rounding)
-          const T esum = a ? e2 + e : e + e2;
-#else
           const T wsum = w + __shfl_xor_sync(0xffffffffu, w, 16);
           const T esum = e + __shfl_xor_sync(0xffffffffu, e, 16);
-#endif
           zmax = fmax(zmax, T(1) - wsum);
           if (a == (k & 1))                               // the two lanes of a sample share the stores
             ubrow[o * S + k] = fma(esum - T(1), A.ubscale, -A.ubpad);
         }
       }
+      // linearisation offset of the final rows: -(x_S - x_f) + d x_S/du . u  (:271)
       const T valp = -(p - (a ? A.xf[1] : A.xf[0])) + tp, valv = -(v - (a ? A.xf[4] : A.xf[3])) + tv;
       const double rp = sum16((double)(active ? valp : T(0)));
       const double rv = sum16((double)(active ? valv : T(0)));
@@ -451,33 +320,39 @@ drone_assemble_kernel(const __grid_constant__ DroneArgs<T, S> A) {
       fence_async_smem();
       __syncwarp();
       if (ub_ptr != nullptr && a == 0) StU::flush(ub_ptr, stage, 0, si, gu, ns);
-#elif SAA_COPY == 4
+#else
       __syncwarp();
       if (ub_ptr != nullptr) StU::copy_vec(ub_ptr, stage, 0, gu, ns, lane);
       __syncwarp();
-#else
-      __syncwarp();
-      if (ub_ptr != nullptr)
-        copy_run8<T, 3 * S, 1>(ub_ptr + ub_off + s0 * (3 * S), stage, ns * 3 * S, lane);
-      __syncwarp();
 #endif
+      if constexpr (MODE == DRONE_FACTOR) {
+        // trajectory part of the factored record (coalesced: 16 samples per 128-byte line)
+        if (active) {
+          T *fp = A.fp + (i64)a * FR * O.mout + (O.first + s);
+#pragma unroll
+          for (int k = 1; k <= S; ++k) st_stream(fp + (i64)(k - 1) * O.mout, P[k]);
+#pragma unroll
+          for (int o = 0; o < 3; ++o) st_stream(fp + (i64)(S + o) * O.mout, q2[o]);
+        }
+      }
     }
 
-    // ---------------- sensitivity chains, two CSC column pairs per pass ---------
-    drone_chain_pairs<T, S, 0>(A, O, P, A22, q2, oca, a21, dtm, stage, wacc, a, si, lane, s0, ns,
-                               active);
+    // ---------------- sensitivity chains, one CSC column pair per control step -
+    drone_chains<T, S, 0, MODE>(A, O, P, A22, q2, oca, a21, dtm, stage, wacc, a, si, lane, s0, ns, active);
   }
 
 #if SAA_COPY == 3
   bulk_wait_all();
 #endif
-  // ---------------- per-block partial sums (fixed order => deterministic) -----
-  __syncthreads();
-  for (int r = threadIdx.x; r < Rd::N; r += WARPS * 32) {
-    double acc = 0.0;
+  if constexpr (MODE != DRONE_EXPAND) {
+    // ---------------- per-block partial sums (fixed order => deterministic) -----
+    __syncthreads();
+    for (int r = threadIdx.x; r < Rd::N; r += WARPS * 32) {
+      double acc = 0.0;
 #pragma unroll
-    for (int w = 0; w < WARPS; ++w) acc += sm.wacc[w][r];
-    A.partials[(i64)blockIdx.x * Rd::N + r] = acc;
+      for (int w = 0; w < WARPS; ++w) acc += sm.wacc[w][r];
+      A.partials[(i64)blockIdx.x * Rd::N + r] = acc;
+    }
   }
 }
 

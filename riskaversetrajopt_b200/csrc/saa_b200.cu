@@ -259,22 +259,25 @@ i64 drone_col_start(int j, int a, int S, i64 M) {
   return (9 * j + 3 * a + 2) + M * (i64)(6 * j * (S - 1) - 3 * j * (j - 1) + 3 * a * (S - 1 - j));
 }
 
-template <typename T>
+// mode: DRONE_FULL (Ax), DRONE_FACTOR (fsp/fp record instead of Ax), DRONE_EXPAND (record -> Ax for
+// samples [s_begin, s_begin + count) of the output geometry)
+template <typename T, int MODE>
 int launch_drone_assemble(saa_handle *h, const double *us, int scp_iter, void *Ax, void *u, void *Z,
-                          double *sums, cudaStream_t st) {
+                          void *fsp, void *fp, i64 s_begin, i64 count, double *sums, cudaStream_t st) {
   using Args = DroneArgs<T, kS>;
   using Smem = DroneSmem<T, kS, kWarps>;
   Args A{};
   A.mass = (const T *)h->d_a; A.dw = (const T *)h->d_b; A.q = (const T *)h->d_c;
-  A.M = h->M_local; A.Mpad = h->Mpad;
-  fill_drone_common<T>(h, us, A.us, A.dt, A.noise_c, A.drag, A.kp, A.kd, A.x0, A.oc);
+  A.M = MODE == DRONE_EXPAND ? count : h->M_local; A.Mpad = h->Mpad;
+  if (us) fill_drone_common<T>(h, us, A.us, A.dt, A.noise_c, A.drag, A.kp, A.kd, A.x0, A.oc);
+  else for (int o = 0; o < 3; ++o) for (int a = 0; a < 2; ++a) A.oc[o][a] = (T)h->dp.obs_positions[o][a];
   for (int i = 0; i < 6; ++i) A.xf[i] = (T)h->dp.x_final[i];
   double mult, pad, scale, bound;
   drone_mult(h, &mult, &pad); drone_relax(h, &scale, &bound);
   const bool relaxed = scp_iter < 2;
   A.escale = (T)(relaxed ? mult * scale : mult);
   A.ubscale = (T)mult; A.ubpad = (T)pad; A.ztol = (T)0;
-  A.Ax = (T *)Ax;
+  A.Ax = (T *)Ax; A.fsp = (T *)fsp; A.fp = (T *)fp; A.s_begin = s_begin;
   const Layout &L = h->lay;
   A.M_out = h->M_out; A.first_out = h->first_out;
   // the kernel derives the column positions in closed form; they must agree with the layout
@@ -285,24 +288,23 @@ int launch_drone_assemble(saa_handle *h, const double *us, int scp_iter, void *A
   A.ub = relaxed ? nullptr : (T *)u;          // relaxed: bounds are the constant +-bound
   A.ub_off = L.row_s0 + h->first_out * L.R;
   A.Z = (T *)Z;
-  const i64 ntiles = (h->M_local + kTileSamples - 1) / kTileSamples;
+  const i64 ntiles = (A.M + kTileSamples - 1) / kTileSamples;
   const int grid = grid_for(h, ntiles, kWarps, kBlocksPerSM);
   // rows [0, grid) of the partial sums come from the assemble kernel, rows [grid, grid + gridz)
   // from the z-axis kernel
   constexpr int kZWarps = 4;
-  const int gridz = SAA_Z_INLINE ? 0
+  const int gridz = MODE == DRONE_EXPAND ? 0
       : (int)std::max<i64>(1, std::min<i64>((h->M_local + kZWarps * 32 - 1) / (kZWarps * 32), (i64)h->n_sms * 2));
   int rc = ensure_scratch(h, (i64)(grid + gridz) * DroneRed<kS>::N);
   if (rc) return rc;
   A.partials = h->d_partials;
-  auto kern = drone_assemble_kernel<T, kS, kWarps>;
+  auto kern = drone_assemble_kernel<T, kS, kWarps, MODE>;
   SAA_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
   kern<<<grid, kWarps * 32, sizeof(Smem), st>>>(A);
   SAA_CUDA(h, cudaGetLastError());
-  if (gridz > 0) {
-    drone_zmean_kernel<T, kS, kZWarps><<<gridz, kZWarps * 32, 0, st>>>(A, h->d_partials + (i64)grid * DroneRed<kS>::N);
-    SAA_CUDA(h, cudaGetLastError());
-  }
+  if (MODE == DRONE_EXPAND) return SAA_OK;
+  drone_zmean_kernel<T, kS, kZWarps><<<gridz, kZWarps * 32, 0, st>>>(A, h->d_partials + (i64)grid * DroneRed<kS>::N);
+  SAA_CUDA(h, cudaGetLastError());
   const int n = DroneRed<kS>::N;
   reduce_partials_kernel<double><<<(n + 3) / 4, 128, 0, st>>>(h->d_partials, grid + gridz, n, sums);
   SAA_CUDA(h, cudaGetLastError());
@@ -602,8 +604,9 @@ int saa_linearize_assemble(saa_handle *h, const double *us, int scp_iter, void *
   if (rc) return rc;
   double *sums = mean_sums ? mean_sums : h->d_sums;
   if (h->problem == SAA_DRONE)
-    rc = h->precision == 64 ? launch_drone_assemble<double>(h, us, scp_iter, Ax, u, Z, sums, st)
-                            : launch_drone_assemble<float>(h, us, scp_iter, Ax, u, Z, sums, st);
+    rc = h->precision == 64
+             ? launch_drone_assemble<double, DRONE_FULL>(h, us, scp_iter, Ax, u, Z, nullptr, nullptr, 0, 0, sums, st)
+             : launch_drone_assemble<float, DRONE_FULL>(h, us, scp_iter, Ax, u, Z, nullptr, nullptr, 0, 0, sums, st);
   else
     rc = h->precision == 64 ? launch_car_assemble<double>(h, us, scp_iter, Ax, u, Z, sums, st)
                             : launch_car_assemble<float>(h, us, scp_iter, Ax, u, Z, sums, st);
@@ -659,6 +662,46 @@ int saa_shared_close(int device, void *ptr) {
 int saa_shared_free(int device, void *ptr) {
   if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, SAA_ERR_CUDA, "cudaSetDevice failed");
   return cudaFree(ptr) == cudaSuccess ? SAA_OK : fail(nullptr, SAA_ERR_CUDA, "cudaFree failed");
+}
+
+int saa_factored_sizes(const saa_handle *h, int64_t *n_sp, int64_t *n_p) {
+  if (!h) return fail(h, SAA_ERR_ARG, "NULL handle");
+  if (h->problem != SAA_DRONE) return fail(h, SAA_ERR_ARG, "the factored record is implemented for the drone");
+  if (n_sp) *n_sp = h->M_out * (i64)(kS * (kS - 1));              // 2 axes x S(S-1)/2 sensitivities
+  if (n_p) *n_p = h->M_out * (i64)(2 * DroneFac<kS>::ROWS);
+  return SAA_OK;
+}
+
+int saa_linearize_factored(saa_handle *h, const double *us, int scp_iter, void *fsp, void *fp, void *u,
+                           void *Z, double *mean_sums, void *stream) {
+  if (!h || !us || !fsp || !fp || !u) return fail(h, SAA_ERR_ARG, "NULL argument");
+  if (h->problem != SAA_DRONE) return fail(h, SAA_ERR_ARG, "the factored record is implemented for the drone");
+  if (!h->params_set || !h->samples_set) return fail(h, SAA_ERR_STATE, "set params and samples first");
+  SAA_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = ensure_scratch(h, 1);
+  if (rc) return rc;
+  double *sums = mean_sums ? mean_sums : h->d_sums;
+  return h->precision == 64
+             ? launch_drone_assemble<double, DRONE_FACTOR>(h, us, scp_iter, nullptr, u, Z, fsp, fp, 0, 0, sums, st)
+             : launch_drone_assemble<float, DRONE_FACTOR>(h, us, scp_iter, nullptr, u, Z, fsp, fp, 0, 0, sums, st);
+}
+
+int saa_expand_factored(saa_handle *h, int scp_iter, const void *fsp, const void *fp, int64_t sample_begin,
+                        int64_t sample_count, void *Ax, void *stream) {
+  if (!h || !fsp || !fp || !Ax) return fail(h, SAA_ERR_ARG, "NULL argument");
+  if (h->problem != SAA_DRONE) return fail(h, SAA_ERR_ARG, "the factored record is implemented for the drone");
+  if (!h->params_set) return fail(h, SAA_ERR_STATE, "set params first");
+  if (sample_begin < 0 || sample_count < 0 || sample_begin + sample_count > h->M_out)
+    return fail(h, SAA_ERR_ARG, "sample range outside the output geometry");
+  if (sample_count == 0) return SAA_OK;
+  SAA_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  return h->precision == 64
+             ? launch_drone_assemble<double, DRONE_EXPAND>(h, nullptr, scp_iter, Ax, nullptr, nullptr, (void *)fsp,
+                                                           (void *)fp, sample_begin, sample_count, nullptr, st)
+             : launch_drone_assemble<float, DRONE_EXPAND>(h, nullptr, scp_iter, Ax, nullptr, nullptr, (void *)fsp,
+                                                          (void *)fp, sample_begin, sample_count, nullptr, st);
 }
 
 int saa_rollout(saa_handle *h, const double *us, void *Xs, void *stream) {

@@ -49,9 +49,6 @@ struct Layout {
 // ----------------------------------------------------------------------------
 template <typename T>
 __device__ __forceinline__ T sum16(T v) {   // sum over the 16 lanes that share lane>>4
-#ifdef SAA_ABL_NOMEAN
-  return v;   // ablation build (timing experiments only): mean rows are wrong
-#endif
   v += __shfl_xor_sync(0xffffffffu, v, 8);
   v += __shfl_xor_sync(0xffffffffu, v, 4);
   v += __shfl_xor_sync(0xffffffffu, v, 2);
@@ -191,10 +188,7 @@ template <typename T, int LEN> struct Stager {
   // unaligned head / tail elements of a run or row go out as scalar stores.
   __device__ __forceinline__ static void copy_vec(T *base, const T *stage, int a, i64 g0, int ns,
                                                   int lane) {
-#ifdef SAA_ABL_NOCOPY
-    if (ns > 1000) base[g0] = stage[lane];   // ablation build (timing experiments only): no output
-    return;
-#endif
+
     const int off = (int)(g0 & (VEC - 1));
     const int head = (VEC - off) & (VEC - 1);
     if (ROWWISE) {

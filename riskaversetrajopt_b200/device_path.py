@@ -216,6 +216,35 @@ class DevicePath:
                                          int(finalize), self._stream()), self._h)
         return b
 
+    # -- factored record (multi-GPU gather, drone) ------------------------------------------
+    def factored_sizes(self):
+        n_sp, n_p = C.c_int64(), C.c_int64()
+        check(lib.saa_factored_sizes(self._h, C.byref(n_sp), C.byref(n_p)), self._h)
+        return n_sp.value, n_p.value
+
+    def linearize_factored(self, us_mat, scp_iter, fsp, fp, u, Z=None):
+        """This rank's block as a factored record (sensitivities + trajectory) written to
+        ``fsp`` / ``fp`` / ``u`` (tensors or raw, possibly peer-mapped, pointers)."""
+        us = self._us(us_mat)
+        ptr = lambda t: t.data_ptr() if torch.is_tensor(t) else int(t)
+        check(lib.saa_linearize_factored(self._h, us.ctypes.data, int(scp_iter), ptr(fsp), ptr(fp), ptr(u),
+                                         None if Z is None else Z.data_ptr(), self.mean_sums.data_ptr(),
+                                         self._stream()), self._h)
+
+    def expand_factored(self, scp_iter, fsp, fp, sample_begin, sample_count, Ax):
+        ptr = lambda t: t.data_ptr() if torch.is_tensor(t) else int(t)
+        check(lib.saa_expand_factored(self._h, int(scp_iter), ptr(fsp), ptr(fp), int(sample_begin),
+                                      int(sample_count), ptr(Ax), self._stream()), self._h)
+
+    def write_constants(self, b, scp_iter, write_shared=True):
+        """(Re)write the iterate-independent entries if the relaxation state of ``b`` changed."""
+        ptr = lambda t: t.data_ptr() if torch.is_tensor(t) else int(t)
+        relaxed = scp_iter < self.relax_threshold()
+        if b.get('const_state') != relaxed:
+            check(lib.saa_write_constants(self._h, int(scp_iter), int(write_shared), ptr(b['Ax']),
+                                          ptr(b['l']), ptr(b['u']), self._stream()), self._h)
+            b['const_state'] = relaxed
+
     def finalize_means(self, b, scp_iter=2):
         """After an all-reduce(sum) of ``mean_sums`` over the ranks."""
         ptr = lambda t: t.data_ptr() if torch.is_tensor(t) else int(t)

@@ -14,6 +14,9 @@ Per SCP iteration:
      * ``'sharded'``  – blocks stay in their owners' HBM (compact matrices),
      * ``'peer'``     – fused gather: every rank's kernel stores straight into rank
        0's global value arrays through peer-mapped (CUDA IPC / NVLink) pointers,
+     * ``'factored'`` – like ``'peer'`` but what crosses NVLink is the factored record
+       (sensitivities + trajectory, 3.4 KB instead of 9.1 KB per sample); rank 0 expands it
+       into the CSC entries with the same instructions a single GPU would use (drone only),
      * ``'nccl'``     – ``gather`` of the compact blocks to rank 0 followed by
        ``saa_merge_shard`` (device-to-device run copies).
 """
@@ -97,8 +100,8 @@ class ShardedAssembler:
     ``M_local, M_global, sample_offset = shard_range(...)``-consistent arguments."""
 
     def __init__(self, path, mode='sharded', group=None):
-        if mode not in ('sharded', 'peer', 'nccl'):
-            raise ValueError("mode must be 'sharded', 'peer' or 'nccl'")
+        if mode not in ('sharded', 'peer', 'factored', 'nccl'):
+            raise ValueError("mode must be 'sharded', 'peer', 'factored' or 'nccl'")
         self.path, self.mode, self.group = path, mode, group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.out = None
@@ -106,7 +109,7 @@ class ShardedAssembler:
             path.set_output_geometry(path.M_local, 0)
         else:
             path.set_output_geometry(path.M_global, path.sample_offset)
-        if mode == 'peer':
+        if mode in ('peer', 'factored'):
             self._setup_peer()
         if mode == 'nccl':
             self._setup_nccl()
@@ -116,13 +119,18 @@ class ShardedAssembler:
         p = self.path
         n_rows, _, nnz = p.pattern_sizes(False)
         npdt = np.float64 if p.bits == 64 else np.float32
-        self.shared = SharedBuffers((nnz, n_rows, n_rows), npdt, p.device, 0, self.group)
-        if self.rank == 0:
-            Ax, l, u = self.shared.tensors
-            self.out = dict(Ax=Ax, l=l, u=u, const_state=None)
-        else:
-            Ax, l, u = self.shared.ptrs       # raw peer pointers into rank 0's HBM
-            self.out = dict(Ax=Ax, l=l, u=u, const_state=None)
+        sizes = [nnz, n_rows, n_rows]
+        if self.mode == 'factored':
+            sizes += list(p.factored_sizes())
+            counts = [None] * self.world
+            dist.all_gather_object(counts, p.M_local, group=self.group)
+            self.counts = counts
+        self.shared = SharedBuffers(sizes, npdt, p.device, 0, self.group)
+        # rank 0: tensors over its own allocations; other ranks: raw peer pointers into rank 0's HBM
+        bufs = self.shared.tensors if self.rank == 0 else self.shared.ptrs
+        self.out = dict(Ax=bufs[0], l=bufs[1], u=bufs[2], const_state=None)
+        if self.mode == 'factored':
+            self.fsp, self.fp = bufs[3], bufs[4]
 
     def _setup_nccl(self):
         p = self.path
@@ -152,9 +160,25 @@ class ShardedAssembler:
     def step(self, us_mat, scp_iter):
         p = self.path
         us = broadcast_controls(us_mat, 0, self.group, device=p.device if dist.get_backend(self.group) == 'nccl' else None)
-        b = p.assemble(us, scp_iter, finalize=False, write_shared=(self.rank == 0 or self.mode != 'peer'),
-                       out=self.out)
+        if self.mode == 'factored' and self.rank != 0:
+            # constants of this rank's sample slice (remote, once per relaxation state), then the
+            # factored record of the block instead of its CSC entries
+            p.write_constants(self.out, scp_iter, write_shared=False)
+            p.linearize_factored(us, scp_iter, self.fsp, self.fp, self.out['u'])
+            b = self.out
+        else:
+            remote = self.mode in ('peer', 'factored')
+            b = p.assemble(us, scp_iter, finalize=False, write_shared=(self.rank == 0 or not remote),
+                           out=self.out)
         all_reduce_sums(p.mean_sums, self.group)
+        if self.mode == 'factored':
+            torch.cuda.current_stream(p.device).synchronize()
+            dist.barrier(group=self.group)            # every record has landed in rank 0's HBM
+            if self.rank == 0:
+                p.expand_factored(scp_iter, self.fsp, self.fp, self.counts[0], p.M_global - self.counts[0],
+                                  b['Ax'])
+                p.finalize_means(b, scp_iter)
+            return b if self.rank == 0 else None
         if self.mode == 'peer':
             # remote stores must have landed before rank 0 consumes the arrays
             torch.cuda.current_stream(p.device).synchronize()

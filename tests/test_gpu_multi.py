@@ -49,7 +49,7 @@ def _worker(rank, world, initfile, M, problem, out):
 
     res = {}
     first, cnt = sd.shard_range(M, world, rank)
-    for mode in ('sharded', 'peer', 'nccl'):
+    for mode in ('sharded', 'peer', 'nccl') + (('factored',) if problem == 'drone' else ()):
         if mode == 'nccl' and M % world:
             continue            # the NCCL gather needs equal shards (ValueError otherwise)
         path = make(first, cnt, M)
@@ -90,10 +90,16 @@ def test_two_ranks_reproduce_single_gpu(problem, M):
     nfin = 6 if problem == 'drone' else 4
     for it in its:
         Ax, l, u = r0[('single', it, 0)]
-        for mode in ('peer', 'nccl'):
-            if mode == 'nccl' and M % 2:
+        for mode in ('peer', 'nccl', 'factored'):
+            if (mode == 'nccl' and M % 2) or (mode == 'factored' and problem != 'drone'):
                 continue
             gAx, gl, gu = r0[(mode, it, 0)]
+            if mode == 'factored':
+                # same instructions form the products on rank 0: bitwise equal to the single-GPU run
+                body_cols = slice(0, per * M + fixed)
+                diff = np.flatnonzero(gAx[body_cols] != Ax[body_cols])
+                # only the <= 117 mean-row entries may differ (summation order across ranks)
+                assert diff.size <= 117, (mode, it, diff.size)
             # u-column block, bounds and the mean rows: same kernel, same samples -> bitwise, except
             # the mean rows (different summation order across ranks)
             assert np.allclose(gAx, Ax, rtol=1e-12, atol=1e-14), (mode, it)
