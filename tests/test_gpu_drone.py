@@ -218,3 +218,26 @@ def test_large_M_sampled_parity_and_properties():
     Zh = Zc.cpu().numpy()
     assert np.isclose(out3[0].item(), np.maximum(Zh + 0.5, 0).sum(), rtol=1e-10)
     assert out3[1].item() == np.count_nonzero(Zh <= 1e-6) and out3[2].item() == Zh.max()
+
+
+def test_monte_carlo_statistics_on_device(drone_seed0):
+    """V@R by selection and AV@R in closed form == the reference's sort / LP definitions."""
+    import torch
+    from riskaversetrajopt_b200 import montecarlo as mc
+    from riskaversetrajopt_b200.drone.drone_risk import Model
+    M = 20_000
+    DWs, masses, obs_Qs = _big_samples(M, seed=3)
+    model = Model(20, DWs, masses, obs_Qs, 'saa', 0.1)
+    us = model.initial_guess_us_mat() + 0.3 * np.random.RandomState(8).randn(20, 3)
+    Z, _ = model.path.cvar_terms(us, 0.0, 1e-6)
+    Zh = Z.cpu().numpy()
+    for alpha in (0.05, 0.1, 0.3):
+        xth = int(np.floor(alpha * M))
+        assert mc.monte_carlo_var(Z, alpha) == np.sort(Zh)[M - xth - 1]        # drone_main_plot.py:649-651
+        # the LP of drone_risk.py:664-695 minimises t + mean((Z-t)^+)/alpha over t: brute force on a grid of
+        # order statistics
+        cand = np.sort(Zh)[M - xth - 50:M - xth + 50]
+        obj = np.array([t + np.maximum(Zh - t, 0).mean() / alpha for t in cand])
+        assert np.isclose(mc.monte_carlo_avar(Z, alpha), obj.min(), rtol=1e-9, atol=1e-12)
+    assert mc.fraction_satisfied(Z) == np.mean(Zh <= 1e-6)
+    assert isinstance(Z, torch.Tensor) and Z.is_cuda
