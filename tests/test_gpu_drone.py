@@ -241,3 +241,43 @@ def test_monte_carlo_statistics_on_device(drone_seed0):
         assert np.isclose(mc.monte_carlo_avar(Z, alpha), obj.min(), rtol=1e-9, atol=1e-12)
     assert mc.fraction_satisfied(Z) == np.mean(Zh <= 1e-6)
     assert isinstance(Z, torch.Tensor) and Z.is_cuda
+
+
+@pytest.mark.parametrize("M,scp_iter", [(50, 2), (37, 0), (1000, 5)])
+def test_factored_record_expands_to_identical_entries(drone_seed0, M, scp_iter):
+    """FACTOR + EXPAND (the multi-GPU gather path) on one GPU: the expanded u-column block is
+    bitwise the one the FULL kernel writes; bounds and mean sums agree too."""
+    import torch
+    from riskaversetrajopt_b200.drone import drone_params as dp
+    from riskaversetrajopt_b200.drone.drone_risk import Model
+    DWs, masses, obs_Qs = _big_samples(M, seed=11) if M > 50 else tuple(x[:M] for x in drone_seed0)
+    model = Model(20, DWs, masses, obs_Qs, 'saa', 0.1)
+    p = model.path
+    us = model.initial_guess_us_mat() + 0.2 * np.random.RandomState(M).randn(20, 3)
+    full = {k: v.clone() for k, v in p.assemble(us, scp_iter).items() if torch.is_tensor(v)}
+    sums_full = p.mean_sums.clone()
+    n_sp, n_p = p.factored_sizes()
+    assert n_sp == 380 * M and n_p == 46 * M
+    fsp = torch.full((n_sp,), float('nan'), dtype=torch.float64, device='cuda')
+    fp = torch.full((n_p,), float('nan'), dtype=torch.float64, device='cuda')
+    n_rows, _, nnz = p.pattern_sizes()
+    Ax = torch.zeros(nnz, dtype=torch.float64, device='cuda')
+    u = torch.full((n_rows,), float('nan'), dtype=torch.float64, device='cuda')
+    p.linearize_factored(us, scp_iter, fsp, fp, u)
+    assert not torch.isnan(fsp).any() and not torch.isnan(fp).any()
+    # expand in two pieces with an odd split point, as a matrix owner does for several ranks
+    cut = M // 3
+    p.expand_factored(scp_iter, fsp, fp, 0, cut, Ax)
+    p.expand_factored(scp_iter, fsp, fp, cut, M - cut, Ax)
+    torch.cuda.synchronize()
+    n_rows_, n_cols, indptr, indices = p.pattern()
+    for c in range(60):
+        j, a = divmod(c, 3)
+        if a == 2 or j > 18:
+            continue
+        lo, hi = indptr[c] + 2, indptr[c + 1] - 1             # skip the final rows and the control row
+        assert torch.equal(Ax[lo:hi], full['Ax'][lo:hi]), c
+    if scp_iter >= 2:
+        lo = 7 + M
+        assert torch.equal(u[lo:lo + 60 * M], full['u'][lo:lo + 60 * M])
+    assert torch.equal(p.mean_sums, sums_full)
