@@ -31,6 +31,67 @@ __device__ __forceinline__ float rsqrt_t(float x) { return rsqrtf(x); }
 __device__ __forceinline__ void sincos_t(double x, double *s, double *c) { sincos(x, s, c); }
 __device__ __forceinline__ void sincos_t(float x, float *s, float *c) { sincosf(x, s, c); }
 
+// FP64 sincos for the FP64-pipe bound friction kernel: 22 FP64-pipe instructions, no D2I/I2D
+// conversions, no FP64 compares or selects; double-precision accuracy on |x| < 1e5 (measured
+// against sincos(): tools/sincos_check.cu).  Quadrant n = rint(x 2/pi) by the 1.5 2^52 shift,
+// three-step Cody-Waite reduction r = x - n pi/2 with FMAs (pi/2 split in three doubles; the FMA
+// forms n * hi exactly), fdlibm minimax kernels on |r| <= pi/4, quadrant fix-up on the integer
+// pipe.  Larger arguments take the library path.
+// Coefficients live in constant memory: FP64 instructions take a constant-bank operand directly,
+// whereas 64-bit immediates would be re-materialised with two moves per use inside the loop.
+__constant__ double kSinCosC[17] = {
+    6.36619772367581382433e-01,                        // 0: 2/pi
+    -1.57079632679489655800e+00,                       // 1: -pi/2 (hi)
+    -6.12323399573676603587e-17,                       // 2: -pi/2 (mid)
+    1.49738490485916983e-33,                           // 3: -pi/2 (lo; this part of pi/2 is negative)
+    1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06,    // 4..9: sin
+    -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01,
+    -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07,   // 10..15: cos
+    2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02,
+    -0.5};
+
+// branch-free core, valid for |x| < 1e5
+__device__ __forceinline__ void sincos_core(double x, double *s, double *c) {
+  const double *K = kSinCosC;
+  const double SHIFT = 6755399441055744.0;                    // 1.5 * 2^52
+  const double t = fma(x, K[0], SHIFT);                       // x * 2/pi, integer part in the low bits
+  const int n = __double2loint(t);
+  const double nf = t - SHIFT;
+  double r = fma(nf, K[1], x);
+  r = fma(nf, K[2], r);
+  r = fma(nf, K[3], r);            // keeps r relatively accurate next to multiples of pi/2
+  const double z = r * r;
+  double ps = fma(z, K[4], K[5]);
+  ps = fma(z, ps, K[6]);
+  ps = fma(z, ps, K[7]);
+  ps = fma(z, ps, K[8]);
+  ps = fma(z, ps, K[9]);
+  const double sn = fma(r * z, ps, r);
+  double pc = fma(z, K[10], K[11]);
+  pc = fma(z, pc, K[12]);
+  pc = fma(z, pc, K[13]);
+  pc = fma(z, pc, K[14]);
+  pc = fma(z, pc, K[15]);
+  const double cs = fma(z * z, pc, fma(z, K[16], 1.0));
+  // n mod 4: 0 (s, c)  1 (c, -s)  2 (-s, -c)  3 (-c, s)
+  const bool swap = n & 1;
+  double so = swap ? cs : sn, co = swap ? sn : cs;
+  const int sflip = (n & 2) << 30, cflip = ((n + 1) & 2) << 30;
+  so = __hiloint2double(__double2hiint(so) ^ sflip, __double2loint(so));
+  co = __hiloint2double(__double2hiint(co) ^ cflip, __double2loint(co));
+  *s = so; *c = co;
+}
+__device__ __forceinline__ void sincos_core(float x, float *s, float *c) { sincosf(x, s, c); }
+// true if the core's reduction does not cover x (|x| >= 1e5, NaN, Inf)
+__device__ __forceinline__ bool sincos_big(double x) { return (__double2hiint(x) & 0x7fffffff) >= 0x40f86a00; }
+__device__ __forceinline__ bool sincos_big(float) { return false; }
+
+__device__ __forceinline__ void sincos_fast(double x, double *s, double *c) {
+  if (sincos_big(x)) sincos(x, s, c);      // library slow path
+  else sincos_core(x, s, c);
+}
+__device__ __forceinline__ void sincos_fast(float x, float *s, float *c) { sincosf(x, s, c); }
+
 template <int S> struct CarRed {
   static constexpr int PX = 0;                    // + c*(S-1) + j    (c<2, j<S-1)
   static constexpr int PY = 2 * (S - 1);          // + c*(S-1) + j

@@ -8,18 +8,33 @@ int launch_hopper(saa_handle *h, int n_c, const double *px, void *mu, void *dmu,
   A.M = h->M_local; A.F = h->n_feat; A.n_c = n_c; A.mu_nom = (T)h->mu_nom;
   for (int c = 0; c < n_c; ++c) A.px[c] = (T)px[c];
   A.mu = (T *)mu; A.dmu = (T *)dmu; A.lambda = lambda;
-  const i64 total = h->M_local * n_c;
+  // chunk of samples staged per block iteration: features (4 arrays) within ~48 KB, and a
+  // multiple of the block size in (sample, contact) pairs when one exists
+  const size_t es = sizeof(T);
+  int cap = (int)std::max<size_t>(1, std::min<size_t>(64, (48 * 1024) / (4 * es * (size_t)h->n_feat)));
+  int chunk = cap;
+  for (int c = cap; c >= std::max(1, cap / 2); --c)
+    if ((c * n_c) % kHopperThreads == 0) { chunk = c; break; }
+  A.chunk = chunk;
+  const size_t smem = 4 * es * (size_t)chunk * h->n_feat + (lambda ? 2 * sizeof(double) * (size_t)chunk * n_c : 0);
+  if (smem > 200 * 1024) return fail(h, SAA_ERR_ARG, "n_features too large for the shared-memory staging");
+  const i64 nchunks = (h->M_local + chunk - 1) / chunk;
+  const int blocks = (int)std::max<i64>(1, std::min<i64>(nchunks, (i64)h->n_sms * 8));
   if (lambda) {
-    int rc = ensure_scratch(h, 2 * total);
+    int rc = ensure_scratch(h, (i64)blocks * 2 * n_c);
     if (rc) return rc;
     A.w = h->d_partials;
+    auto kern = hopper_friction_kernel<T, true>;
+    SAA_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<blocks, kHopperThreads, smem, st>>>(A);
+  } else {
+    auto kern = hopper_friction_kernel<T, false>;
+    SAA_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<blocks, kHopperThreads, smem, st>>>(A);
   }
-  const int threads = 256;
-  const int blocks = (int)std::max<i64>(1, std::min<i64>((total + threads - 1) / threads, (i64)h->n_sms * 8));
-  hopper_friction_kernel<T><<<blocks, threads, 0, st>>>(A);
   SAA_CUDA(h, cudaGetLastError());
   if (lambda) {
-    hopper_reduce_kernel<<<2 * n_c, 256, 0, st>>>(h->d_partials, h->M_local, n_c, hess_sums);
+    hopper_reduce_kernel<<<(2 * n_c * 32 + 255) / 256, 256, 0, st>>>(h->d_partials, blocks, n_c, hess_sums);
     SAA_CUDA(h, cudaGetLastError());
   }
   return SAA_OK;

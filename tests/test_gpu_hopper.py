@@ -88,3 +88,32 @@ def test_large_M_and_fp32():
     m32 = hp.Model(M, 'saa', 0.1, f, precision='fp32')
     g32 = m32.slip_risk_constraints(Z)
     assert np.allclose(g32, b.g(Z), rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("pscale,atol", [(1.0, 1e-13), (2.0e4, 2e-10), (1.0e7, 2e-7)])
+def test_friction_field_argument_ranges(pscale, atol):
+    """The kernel's branch-free sincos covers |theta p + tau| < 1e5; a chunk of samples whose
+    arguments may exceed that takes the library routine.  pscale = 2e4 puts the arguments on both
+    sides of the switch (theta in [0, pi)), 1e7 far beyond it.  The tolerance follows the argument
+    rounding: the oracle rounds theta*p and the sum separately, the kernel uses one FMA, so the
+    arguments differ by up to ulp(|x|) and mu by up to sum_f I_f ulp(|x|)."""
+    from oracle.oracle_hopper import HopperOracleB
+    from riskaversetrajopt_b200.hopper import hopper as hp
+    M = 4099                                    # ragged: not a multiple of the staged chunk
+    rs = np.random.RandomState(11)
+    f = (0.025 * np.sqrt(2 / 30) * rs.uniform(0, 1, (M, 30)), rs.uniform(0, np.pi, (M, 30)),
+         rs.uniform(0, 2 * np.pi, (M, 30)))
+    f[1][::7] *= 1e-3                           # some samples stay in the fast range at pscale = 2e4
+    m = hp.Model(M, 'saa', 0.1, f)
+    b = HopperOracleB(M, 'saa', 0.1, *f)
+    px = pscale * rs.uniform(-1, 1, 20)
+    lam = rs.randn(M, 20)
+    mu, dmu, hs = m._friction(px, lam.reshape(-1))
+    mu_b, dmu_b, d2mu_b = b.friction(px)
+    assert np.allclose(mu, mu_b, rtol=1e-9, atol=atol)
+    assert np.allclose(dmu, dmu_b, rtol=1e-9, atol=atol * np.pi)
+    assert np.allclose(hs[:, 0], (lam * dmu_b).sum(0), rtol=1e-9, atol=atol * np.pi * M)
+    assert np.allclose(hs[:, 1], (lam * d2mu_b).sum(0), rtol=1e-9, atol=atol * np.pi ** 2 * M)
+    # determinism: the Hessian sums are reduced in a fixed order
+    _, _, hs2 = m._friction(px, lam.reshape(-1))
+    assert np.array_equal(hs, hs2)

@@ -4,7 +4,13 @@ rep = sys.argv[1]
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + (["-k", sys.argv[2]] if len(sys.argv) > 2 else []),
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(src.splitlines()))
-hdr = rows[1]; data = [r for r in rows[2:] if len(r) == len(hdr)]
+hdr = rows[1]
+data = []
+for r in rows[2:]:
+    if r and r[0] == 'Kernel Name' and data:
+        break                      # several captures in the report: keep the first
+    if len(r) == len(hdr) and r[0] != 'Address':
+        data.append(r)
 ci = {h: i for i, h in enumerate(hdr)}
 tot = sum(int(r[ci['# Samples']]) for r in data)
 print(len(data), "SASS instructions;", tot, "samples")
