@@ -12,14 +12,13 @@
 //   d(p+,v+)/d(p,v) = [[1, dt], [a21, a22_k]],  a21 = -kp dt/m,
 //   a22_k = 1 - dt (kd + 2c|v_k|)/m,   d v+/du = dt/m.
 //
-// Thread mapping: one warp owns a tile of 15 samples plus one HALO sample (the next tile's
-// first sample, computed redundantly so that every 128-byte line of a column is written whole by
-// one warp: "line ownership", saa_common.cuh); lanes 0-15 run the x axis of those 16 samples,
-// lanes 16-31 the y axis (the z axis only feeds the sample-mean rows: drone_zmean_kernel).  For
-// each control step j the lane runs the sensitivity chain k = j+1..S in registers and stages the
-// 3*(S-1-j) CSC entries of its sample for column (j, axis) in shared memory; the warp then streams
-// the lines it owns of the two column sub-runs to global memory, consecutive lanes on consecutive
-// 16-byte chunks.
+// Thread mapping: one warp owns a tile of 16 samples; lanes 0-15 run the x axis
+// of those samples, lanes 16-31 the y axis (the z axis only feeds the sample-mean
+// rows: drone_zmean_kernel).  For each control step j the lane runs the
+// sensitivity chain k = j+1..S in registers and stages the 3*(S-1-j) CSC entries
+// of its sample for column (j, axis) in shared memory; the warp then streams the
+// two column sub-runs (16 samples x 3*(S-1-j) contiguous doubles each) to global
+// memory, consecutive lanes on consecutive 16-byte chunks.
 //
 // Three modes of the same kernel:
 //   FULL    rollout -> chains -> CSC entries                       (single GPU, or a rank's own block)
@@ -36,7 +35,8 @@
 // ---- tuning switches (defaults = the measured best; history in profiles/README.md) ----
 #ifndef SAA_COPY
 #define SAA_COPY 4         // 4: 16-byte shared loads -> 16-byte streaming stores; 3: TMA bulk stores
-                           // (cp.async.bulk with an evict-first hint) for the densely staged columns
+                           // (cp.async.bulk, correct but measured 2-3x slower on these short,
+                           // 16-byte-aligned runs)
 #endif
 #ifndef SAA_BPS
 #define SAA_BPS 2          // resident blocks per SM the kernel is compiled for
@@ -98,7 +98,13 @@ template <int S, int J> struct DroneChain {
 
 template <typename T, int S, int WARPS>
 struct DroneSmem {
-  static constexpr int STAGE = 2 * kTileSamples * (3 * S + 2) + 8;   // >= every Stager<T,LEN>::SIZE
+  static constexpr int HALF = 2 * kTileSamples * (3 * S + 2) + 8;   // one staging buffer (>= every Stager<T,LEN>::SIZE)
+#if SAA_COPY == 3
+  static constexpr int STAGE = 2 * HALF;   // TMA copy-out is double buffered: the engine drains one
+                                           // column pair while the warp computes the next
+#else
+  static constexpr int STAGE = HALF;
+#endif
   T stage[WARPS][STAGE];
   double wacc[WARPS][DroneRed<S>::N];
 };
@@ -110,32 +116,21 @@ template <typename T> struct DroneOut {
   i64 mout, first;
 };
 
-// stage -> global for one column pair: g0x / g0y = global element of the tile's first own sample in
-// the x / y column, n_own = own elements per column; first / last tile of the launch write exactly
-// their own elements at that end (there is no neighbour to own the partial line)
+// stage -> global for one column pair
 template <typename T, int LEN>
-__device__ __forceinline__ void drone_flush(T *base, T *stg, i64 g0x, i64 g0y, int n_own, bool first,
-                                            bool last, int a, int si, int lane) {
+__device__ __forceinline__ void drone_flush(T *base, T *stg, i64 g0x, i64 g0y, int a, int si, int ns,
+                                            int lane) {
   using St = Stager<T, LEN>;
-  i64 e0x, e1x, e0y, e1y;
-  St::span(g0x, n_own, first, last, e0x, e1x);
-  St::span(g0y, n_own, first, last, e0y, e1y);
 #if SAA_COPY == 3
-  if constexpr (!St::ROWWISE) {
-    fence_async_smem();
-    __syncwarp();
-    if (si == 0) {
-      if (a == 0) St::bulk_lines(base, stg, 0, g0x, e0x, e1x);
-      else St::bulk_lines(base, stg, 1, g0y, e0y, e1y);
-    }
-    bulk_commit();
-    return;
-  }
+  fence_async_smem();
+  __syncwarp();
+  St::flush(base, stg, a, si, a ? g0y : g0x, ns);
+#else
+  __syncwarp();
+  St::copy_vec(base, stg, 0, g0x, ns, lane);
+  St::copy_vec(base, stg, 1, g0y, ns, lane);
+  __syncwarp();
 #endif
-  __syncwarp();
-  St::copy_lines(base, stg, 0, g0x, e0x, e1x, lane);
-  St::copy_lines(base, stg, 1, g0y, e0y, e1y, lane);
-  __syncwarp();
 }
 
 // ---- sensitivity chains, one CSC column pair (x and y column of control step J) per pass ----
@@ -143,21 +138,26 @@ template <typename T, int S, int J, int MODE>
 __device__ __forceinline__ void drone_chains(const DroneArgs<T, S> &A, const DroneOut<T> &O,
                                              const T (&P)[S + 1], const T (&A22)[S],
                                              const T (&q2)[3], const T (&oca)[3], T a21, T dtm,
-                                             T *stage, double *wacc, int a, int si, int srow, int lane,
-                                             i64 s0, int nown, bool first, bool last, bool own) {
+                                             T *stage, double *wacc, int a, int si, int lane, i64 s0,
+                                             int ns, bool active) {
   using Rd = DroneRed<S>;
   if constexpr (J >= S - 1) {
     // last control step: no sample rows, only d v_S/du = dt/m enters the mean rows
     if constexpr (MODE != DRONE_EXPAND) {
-      const double rv = sum16((double)(own ? dtm : T(0)));
+      const double rv = sum16((double)(active ? dtm : T(0)));
       if (si == 0) wacc[Rd::FIN_V + a * S + (S - 1)] += rv;
     }
   } else {
     using C = DroneChain<S, J>;
     constexpr int SLEN = (MODE == DRONE_FACTOR) ? C::L : C::LEN;   // staged values per sample
     using St = Stager<T, SLEN>;
-    static_assert(St::SIZE <= DroneSmem<T, S, 1>::STAGE, "staging buffer too small");
+    static_assert(St::SIZE <= DroneSmem<T, S, 1>::HALF, "staging buffer too small");
+#if SAA_COPY == 3
+    // upper bounds went through buffer 0, chain 0 takes buffer 1, chain 1 buffer 0, ...
+    T *const stg = stage + ((J & 1) ? 0 : DroneSmem<T, S, 1>::HALF);
+#else
     T *const stg = stage;
+#endif
     // optimisation barriers: keep per-chain coefficient math from being hoisted (common
     // subexpressions across the unrolled chains would cost ~60 live doubles), and recompute the
     // column bases per chain (2 IMADs) instead of keeping 2(S-1) of them live
@@ -170,11 +170,11 @@ __device__ __forceinline__ void drone_chains(const DroneArgs<T, S> &A, const Dro
     const i64 g0x = C::CA0 + mout * C::CB0 + sbase * C::LEN, g0y = C::CA1 + mout * C::CB1 + sbase * C::LEN;
     T *mine = St::mine(stg, a, si, MODE == DRONE_FACTOR ? (a ? f0y : f0x) : (a ? g0y : g0x));
 #if SAA_COPY == 3
-    bulk_wait_read();              // the copy engine has read the previous column pair out of the buffer
+    bulk_wait_read1();             // the column pair staged two steps ago has left this buffer
     __syncwarp();
 #endif
     T sp = T(0), sv = dtm;         // d(p,v)_{J+1}/du_J = (0, dt/m)
-    const T *fin = O.fsp + (a ? f0y : f0x) + (i64)srow * C::L;   // EXPAND: this sample's chain
+    const T *fin = O.fsp + (a ? f0y : f0x) + (i64)(active ? si : 0) * C::L;   // EXPAND: this sample's chain
 #pragma unroll
     for (int k = J + 1; k < S; ++k) {
       const int kk = k - J - 1;
@@ -197,15 +197,14 @@ __device__ __forceinline__ void drone_chains(const DroneArgs<T, S> &A, const Dro
     }
     if constexpr (MODE != DRONE_EXPAND) {
       // sample-mean rows: d p_S/du_J, d v_S/du_J summed over the tile
-      const double rp = sum16((double)(own ? sp : T(0)));
-      const double rv = sum16((double)(own ? sv : T(0)));
+      const double rp = sum16((double)(active ? sp : T(0)));
+      const double rv = sum16((double)(active ? sv : T(0)));
       if (si == 0) { wacc[Rd::FIN_P + a * (S - 1) + J] += rp; wacc[Rd::FIN_V + a * S + J] += rv; }
     }
-    // the factored record keeps exact runs (its reader is the EXPAND launch of another rank)
-    if constexpr (MODE == DRONE_FACTOR) drone_flush<T, SLEN>(O.fsp, stg, f0x, f0y, nown * SLEN, true, true, a, si, lane);
-    else drone_flush<T, SLEN>(O.Ax, stg, g0x, g0y, nown * SLEN, first, last, a, si, lane);
-    drone_chains<T, S, J + 1, MODE>(A, O, P, A22, q2, oca, a21, dtm, stage, wacc, a, si, srow, lane, s0,
-                                    nown, first, last, own);
+    if constexpr (MODE == DRONE_FACTOR) drone_flush<T, SLEN>(O.fsp, stg, f0x, f0y, a, si, ns, lane);
+    else drone_flush<T, SLEN>(O.Ax, stg, g0x, g0y, a, si, ns, lane);
+    drone_chains<T, S, J + 1, MODE>(A, O, P, A22, q2, oca, a21, dtm, stage, wacc, a, si, lane, s0, ns,
+                                    active);
   }
 }
 
@@ -234,18 +233,14 @@ drone_assemble_kernel(const __grid_constant__ DroneArgs<T, S> A) {
   i64 ub_base = (i64)A.ub, ub_off = A.ub_off;
   opaque(ub_base); opaque(ub_off);
   T *const ub_ptr = (T *)ub_base;
-  const i64 ntiles = (A.M + kTileOwn - 1) / kTileOwn;
+  const i64 ntiles = (A.M + kTileSamples - 1) / kTileSamples;
   const i64 tstride = (i64)gridDim.x * WARPS;
 #pragma unroll 1
   for (i64 tile = (i64)blockIdx.x * WARPS + warp; tile < ntiles; tile += tstride) {
-    // rows 0..14: the tile's own samples; row 15: halo = first sample of the next tile
-    const i64 s0 = tile * kTileOwn;
-    const int nown = (int)min((i64)kTileOwn, A.M - s0);
-    const bool first = tile == 0, last = tile == ntiles - 1;
-    const bool active = s0 + si < A.M;          // the row's sample exists
-    const bool own = active && si < kTileOwn;   // ... and belongs to this tile (sums, Z, record)
-    const int srow = active ? si : 0;
-    const i64 s = s0 + srow;
+    const i64 s0 = tile * kTileSamples;
+    const int ns = (int)min((i64)kTileSamples, A.M - s0);
+    const bool active = si < ns;
+    const i64 s = s0 + (active ? si : 0);
     T P[S + 1], A22[S];
     T q2[3], oca[3];
 #pragma unroll
@@ -287,7 +282,7 @@ drone_assemble_kernel(const __grid_constant__ DroneArgs<T, S> A) {
       const i64 gu = ub_off + s0 * (3 * S);
       T *ubrow = StU::mine(stage, 0, si, gu);
 #if SAA_COPY == 3
-      bulk_wait_read();            // the previous tile's last column pair has left the buffer
+      bulk_wait_read1();           // buffer 0 was last used by the second-to-last column pair of the previous tile
       __syncwarp();
 #endif
 #pragma unroll
@@ -317,20 +312,22 @@ drone_assemble_kernel(const __grid_constant__ DroneArgs<T, S> A) {
       }
       // linearisation offset of the final rows: -(x_S - x_f) + d x_S/du . u  (:271)
       const T valp = -(p - (a ? A.xf[1] : A.xf[0])) + tp, valv = -(v - (a ? A.xf[4] : A.xf[3])) + tv;
-      const double rp = sum16((double)(own ? valp : T(0)));
-      const double rv = sum16((double)(own ? valv : T(0)));
+      const double rp = sum16((double)(active ? valp : T(0)));
+      const double rv = sum16((double)(active ? valv : T(0)));
       if (si == 0) { wacc[Rd::VAL + a] += rp; wacc[Rd::VAL + 3 + a] += rv; }
-      if (A.Z != nullptr && a == 0 && own) A.Z[s] = zmax - A.ztol;
+      if (A.Z != nullptr && a == 0 && active) A.Z[s] = zmax - A.ztol;
+#if SAA_COPY == 3
+      fence_async_smem();
       __syncwarp();
-      if (ub_ptr != nullptr) {
-        i64 e0, e1;
-        StU::span(gu, nown * 3 * S, first, last, e0, e1);
-        StU::copy_lines(ub_ptr, stage, 0, gu, e0, e1, lane);
-      }
+      if (ub_ptr != nullptr && a == 0) StU::flush(ub_ptr, stage, 0, si, gu, ns);
+#else
       __syncwarp();
+      if (ub_ptr != nullptr) StU::copy_vec(ub_ptr, stage, 0, gu, ns, lane);
+      __syncwarp();
+#endif
       if constexpr (MODE == DRONE_FACTOR) {
-        // trajectory part of the factored record (coalesced: 15 samples per 128-byte line)
-        if (own) {
+        // trajectory part of the factored record (coalesced: 16 samples per 128-byte line)
+        if (active) {
           T *fp = A.fp + (i64)a * FR * O.mout + (O.first + s);
 #pragma unroll
           for (int k = 1; k <= S; ++k) st_stream(fp + (i64)(k - 1) * O.mout, P[k]);
@@ -341,8 +338,7 @@ drone_assemble_kernel(const __grid_constant__ DroneArgs<T, S> A) {
     }
 
     // ---------------- sensitivity chains, one CSC column pair per control step -
-    drone_chains<T, S, 0, MODE>(A, O, P, A22, q2, oca, a21, dtm, stage, wacc, a, si, srow, lane, s0, nown,
-                                first, last, own);
+    drone_chains<T, S, 0, MODE>(A, O, P, A22, q2, oca, a21, dtm, stage, wacc, a, si, lane, s0, ns, active);
   }
 
 #if SAA_COPY == 3

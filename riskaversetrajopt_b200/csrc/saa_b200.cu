@@ -288,7 +288,7 @@ int launch_drone_assemble(saa_handle *h, const double *us, int scp_iter, void *A
   A.ub = relaxed ? nullptr : (T *)u;          // relaxed: bounds are the constant +-bound
   A.ub_off = L.row_s0 + h->first_out * L.R;
   A.Z = (T *)Z;
-  const i64 ntiles = (A.M + kTileOwn - 1) / kTileOwn;
+  const i64 ntiles = (A.M + kTileSamples - 1) / kTileSamples;
   const int grid = grid_for(h, ntiles, kWarps, kBlocksPerSM);
   // rows [0, grid) of the partial sums come from the assemble kernel, rows [grid, grid + gridz)
   // from the z-axis kernel

@@ -12,8 +12,7 @@ namespace saa {
 
 typedef long long i64;
 
-constexpr int kTileSamples = 16;   // sample rows per warp tile: lanes = 16 samples x 2 "roles"
-constexpr int kTileOwn = 15;       // drone: rows 0..14 are the tile's own samples, row 15 the halo (Stager)
+constexpr int kTileSamples = 16;   // samples per warp tile: lanes = 16 samples x 2 "roles"
 constexpr int kSMs = 148;          // B200
 
 // ----------------------------------------------------------------------------
@@ -114,15 +113,23 @@ __device__ __forceinline__ void copy_run(T *__restrict__ dst, const T *__restric
 // Both addresses must be 16-byte aligned and the size a multiple of 16 bytes.
 // ----------------------------------------------------------------------------
 __device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, unsigned bytes) {
+#ifdef SAA_TMA_HINT
   // L2 evict-first policy (the encoding CUTLASS uses for TMA::CacheHintSm90::EVICT_FIRST): the
-  // assembled values are never re-read by this kernel; without the hint the same stores ran 2.2x slower
+  // assembled values are never re-read by this kernel
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst),
                "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes), "l"(0x12F0000000000000ull)
                : "memory");
+#else
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+               "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+               : "memory");
+#endif
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all of this thread's bulk groups have finished READING shared memory (buffer reusable)
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... all but the most recent group (double-buffered staging)
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // make this thread's generic-proxy shared-memory writes visible to the async proxy (TMA)
 __device__ __forceinline__ void fence_async_smem() {
@@ -132,26 +139,16 @@ __device__ __forceinline__ void fence_async_smem() {
 }
 
 // Staging geometry of one CSC column pair (x and y column of a control step):
-// kTileSamples sample rows of LEN values per column.
-//  * dense (row stride LEN): conflict-free 64-bit stores for odd LEN, 2-way for LEN = 2 (mod 4).
-//  * row-wise (LEN = 0 mod 4 would be 4..16-way conflicted when dense): padded row stride LEN + VEC.
-// A run that starts at global element g0 is staged at offset (g0 mod VEC) so that 16-byte aligned
-// global addresses map to 16-byte aligned shared addresses.
-//
-// LINE OWNERSHIP.  The runs of neighbouring tiles abut at arbitrary 8-byte offsets, so a tile that
-// writes exactly its own elements leaves a partially written 128-byte line at either end of every
-// run, completed later by another warp -- measured (tools/wbw3.cu) such partial-line writes cost
-// ~3.4 full-line writes each in L2.  Instead the last of the kTileSamples rows is a HALO: a copy
-// of the next tile's first sample, computed redundantly by this warp.  A tile then writes every line
-// that STARTS inside its own run, whole (the last one extends up to LINE-1 elements into the halo
-// row), and nothing before its first line start: every line of the column is written exactly once,
-// by one warp, with line-aligned 16-byte vector stores.  This needs LEN >= LINE-1 (one halo row
-// covers the overhang); shorter columns, and the first / last tile of a launch, fall back to
-// writing exactly their own elements.
+// 16 sample rows of LEN values per column.
+//  * dense (row stride LEN): one bulk store per column run.  Conflict-free 64-bit
+//    stores for odd LEN, 2-way for LEN = 2 (mod 4).
+//  * row-wise (LEN = 0 mod 4 would be 4..16-way conflicted when dense): padded row
+//    stride LEN + VEC, every lane bulk-stores its own row.
+// A run that starts at global element g0 is staged at offset (g0 mod VEC) so that
+// 16-byte aligned global addresses map to 16-byte aligned shared addresses; the
+// (< VEC) head / tail elements go out as plain stores.
 template <typename T, int LEN> struct Stager {
   static constexpr int VEC = 16 / (int)sizeof(T);
-  static constexpr int LINE = 128 / (int)sizeof(T);
-  static constexpr bool OWN_LINES = LEN >= LINE - 1;
 #ifdef SAA_TMA_DENSE_ONLY
   static constexpr bool ROWWISE = false;
 #else
@@ -166,89 +163,86 @@ template <typename T, int LEN> struct Stager {
     return ROWWISE ? stage + (a * kTileSamples + si) * RSTRIDE + off
                    : stage + a * YBASE + off + si * LEN;
   }
-
-  // [e0, e1): global elements this tile writes of a run whose own part is [g0, g0 + n_own)
-  __device__ __forceinline__ static void span(i64 g0, int n_own, bool first, bool last, i64 &e0, i64 &e1) {
-    if (OWN_LINES) {
-      e0 = first ? g0 : ((g0 + LINE - 1) & ~(i64)(LINE - 1));
-      e1 = last ? g0 + n_own : ((g0 + n_own + LINE - 1) & ~(i64)(LINE - 1));
-    } else {
-      e0 = g0; e1 = g0 + n_own;
-    }
-  }
-
-  // staged element i (i = global element - g0) of column a
-  __device__ __forceinline__ static const T &elem(const T *stage, int a, int off, int i) {
-    if (ROWWISE) {
-      const int row = (int)((unsigned)i / (unsigned)LEN), col = i - row * LEN;
-      return stage[(a * kTileSamples + row) * RSTRIDE + off + col];
-    }
-    return stage[a * YBASE + off + i];
-  }
-
-  // Warp-cooperative copy of the staged elements [e0 - g0, e1 - g0) of column a to base[e0, e1):
-  // 16-byte shared loads -> 16-byte streaming stores, consecutive lanes on consecutive 16-byte
-  // chunks (4 whole lines per instruction when e0 is line aligned); the (< VEC) elements in front
-  // of / behind the 16-byte aligned part go out as scalar stores.
-  __device__ __forceinline__ static void copy_lines(T *base, const T *stage, int a, i64 g0, i64 e0, i64 e1,
-                                                    int lane) {
+  // call after fence_async_smem() + __syncwarp(); g0 = global element index (in `base`) of the
+  // tile's run of column a; ns = valid sample rows
+  __device__ __forceinline__ static void flush(T *base, T *stage, int a, int si, i64 g0, int ns) {
     const int off = (int)(g0 & (VEC - 1));
-    const int n = (int)(e1 - e0), i0 = (int)(e0 - g0);
-    const int head = (int)((VEC - (e0 & (VEC - 1))) & (VEC - 1));
-    const int h = head < n ? head : n;
-    const int nvec = (n - h) / VEC, tail = n - h - nvec * VEC;
-    T *dst = base + e0;
-    if (lane < h) st_stream(dst + lane, elem(stage, a, off, i0 + lane));
-    if (lane < tail) st_stream(dst + h + nvec * VEC + lane, elem(stage, a, off, i0 + h + nvec * VEC + lane));
-    int4 *dst4 = reinterpret_cast<int4 *>(dst + h);
+    const int head = (VEC - off) & (VEC - 1);
     if (ROWWISE) {
-      const T *src0 = stage + a * kTileSamples * RSTRIDE + off;
+      if (si < ns) {
+        T *row = stage + (a * kTileSamples + si) * RSTRIDE + off;
+        T *dst = base + g0 + (i64)si * LEN;
+        constexpr int dummy = 0; (void)dummy;
+        const int bulk = ((LEN - head) / VEC) * VEC, tail = LEN - head - bulk;
+        bulk_store(dst + head, row + head, bulk * (unsigned)sizeof(T));
+        for (int e = 0; e < head; ++e) st_stream(dst + e, row[e]);
+        for (int e = 0; e < tail; ++e) st_stream(dst + head + bulk + e, row[head + bulk + e]);
+      }
+    } else if (si == 0) {
+      const int n = ns * LEN;
+      T *run = stage + a * YBASE + off;
+      T *dst = base + g0;
+      const int h = head < n ? head : n;
+      const int bulk = ((n - h) / VEC) * VEC, tail = n - h - bulk;
+      if (bulk > 0) bulk_store(dst + h, run + h, bulk * (unsigned)sizeof(T));
+      for (int e = 0; e < h; ++e) st_stream(dst + e, run[e]);
+      for (int e = 0; e < tail; ++e) st_stream(dst + h + bulk + e, run[h + bulk + e]);
+    }
+    bulk_commit();
+  }
+
+  // Warp-cooperative copy of column a's staged run with 16-byte shared loads and 16-byte
+  // streaming global stores (consecutive lanes -> consecutive 16-byte chunks); the (< VEC)
+  // unaligned head / tail elements of a run or row go out as scalar stores.
+  __device__ __forceinline__ static void copy_vec(T *base, const T *stage, int a, i64 g0, int ns,
+                                                  int lane) {
+
+    const int off = (int)(g0 & (VEC - 1));
+    const int head = (VEC - off) & (VEC - 1);
+    if (ROWWISE) {
+      constexpr int NVMAX = LEN / VEC > 0 ? LEN / VEC : 1;   // vectors per row when off == 0
+      const int nv = (LEN - head) / VEC;                     // LEN % VEC == 0: nv = NVMAX or NVMAX - 1
+      const int tail = LEN - head - nv * VEC;
+      const T *src0 = stage + a * kTileSamples * RSTRIDE + off + head;
+      T *dst0 = base + g0 + head;
+      const int total = ns * nv;
+      constexpr unsigned MAGIC0 = (unsigned)((0x100000000ull + NVMAX - 1) / NVMAX);
+      constexpr unsigned MAGIC1 = NVMAX > 1 ? (unsigned)((0x100000000ull + NVMAX - 2) / (NVMAX - 1)) : 0u;
+      const unsigned magic = head ? MAGIC1 : MAGIC0;
 #pragma unroll 4
-      for (int v = lane; v < nvec; v += 32) {
-        const int i = i0 + h + v * VEC;
-        const int row = (int)((unsigned)i / (unsigned)LEN), col = i - row * LEN;
-        const T *p = src0 + row * RSTRIDE + col;
-        int4 val;
-        if (col + VEC <= LEN) {
-          val = *reinterpret_cast<const int4 *>(p);
-        } else {                                   // the vector straddles two sample rows
-          T tmp[VEC];
-#pragma unroll
-          for (int q = 0; q < VEC; ++q) tmp[q] = (col + q < LEN) ? p[q] : p[q + RSTRIDE - LEN];
-          val = *reinterpret_cast<const int4 *>(tmp);
-        }
+      for (int v = lane; v < total; v += 32) {
+        const int row = (int)__umulhi((unsigned)v, magic);
+        const int idx = v - row * nv;
+        const int4 val = *reinterpret_cast<const int4 *>(src0 + row * RSTRIDE + idx * VEC);
 #ifdef SAA_PLAIN_ST
-        dst4[v] = val;
+        *reinterpret_cast<int4 *>(dst0 + (i64)row * LEN + idx * VEC) = val;
 #else
-        __stcs(dst4 + v, val);
+        __stcs(reinterpret_cast<int4 *>(dst0 + (i64)row * LEN + idx * VEC), val);
 #endif
       }
+      if (lane < ns) {
+        const T *row = stage + (a * kTileSamples + lane) * RSTRIDE + off;
+        T *dst = base + g0 + (i64)lane * LEN;
+        for (int e = 0; e < head; ++e) st_stream(dst + e, row[e]);
+        for (int e = 0; e < tail; ++e) st_stream(dst + head + nv * VEC + e, row[head + nv * VEC + e]);
+      }
     } else {
-      const int4 *src4 = reinterpret_cast<const int4 *>(stage + a * YBASE + off + i0 + h);
+      const int n = ns * LEN;
+      const T *run = stage + a * YBASE + off;
+      T *dst = base + g0;
+      const int h = head < n ? head : n;
+      const int nvec = (n - h) / VEC, tail = n - h - nvec * VEC;
+      const int4 *src4 = reinterpret_cast<const int4 *>(run + h);
+      int4 *dst4 = reinterpret_cast<int4 *>(dst + h);
 #pragma unroll 4
 #ifdef SAA_PLAIN_ST
       for (int v = lane; v < nvec; v += 32) dst4[v] = src4[v];
 #else
       for (int v = lane; v < nvec; v += 32) __stcs(dst4 + v, src4[v]);
 #endif
+      if (lane < h) st_stream(dst + lane, run[lane]);
+      if (lane < tail) st_stream(dst + h + nvec * VEC + lane, run[h + nvec * VEC + lane]);
     }
-  }
-
-  // TMA variant for dense staging: ONE lane hands the 16-byte aligned part of the span to the copy
-  // engine (cp.async.bulk shared -> global, evict-first) and writes the scalar ends; call after
-  // fence_async_smem() + __syncwarp().  The caller commits the bulk group.
-  __device__ __forceinline__ static void bulk_lines(T *base, const T *stage, int a, i64 g0, i64 e0, i64 e1) {
-    static_assert(!ROWWISE, "bulk stores need the dense layout");
-    const int off = (int)(g0 & (VEC - 1));
-    const int n = (int)(e1 - e0), i0 = (int)(e0 - g0);
-    const int head = (int)((VEC - (e0 & (VEC - 1))) & (VEC - 1));
-    const int h = head < n ? head : n;
-    const int nvec = (n - h) / VEC, tail = n - h - nvec * VEC;
-    const T *run = stage + a * YBASE + off + i0;
-    T *dst = base + e0;
-    if (nvec > 0) bulk_store(dst + h, run + h, (unsigned)(nvec * VEC * sizeof(T)));
-    for (int e = 0; e < h; ++e) st_stream(dst + e, run[e]);
-    for (int e = 0; e < tail; ++e) st_stream(dst + h + nvec * VEC + e, run[h + nvec * VEC + e]);
   }
 };
 

@@ -72,6 +72,22 @@ __global__ void probe(double *dst, i64 M, int tile) {
   }
 }
 
+// car geometry: 2 x 19 columns with sample runs of S-1-J doubles (csrc/car_kernels.cuh, CarCol)
+__global__ void probe_car(double *dst, i64 M, int tile) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const i64 nt = (M + tile - 1) / tile;
+  for (i64 t = (i64)blockIdx.x * nw + warp; t < nt; t += (i64)gridDim.x * nw) {
+    const i64 s0 = t * tile;
+    const int ns = (int)min((i64)tile, M - s0);
+    for (int J = 0; J < S - 1; ++J)
+      for (int c = 0; c < 2; ++c) {
+        const int L = S - 1 - J;
+        const i64 base = 8 * J + 3 + 4 * c + M * (2ll * J * (S - 1) - (i64)J * (J - 1) + (c ? L : 0));
+        write_run(dst, base + s0 * L, ns * L, lane, 32, (double)J);
+      }
+  }
+}
+
 int main() {
   const i64 M = 1000000;
   const i64 total = 1140 * M + 1024;
@@ -96,5 +112,18 @@ int main() {
     }
     printf("%5d %9d %9d %6d %10.0f\n", c.mode, c.warps, c.bps, c.tile, 1140.0 * M * 8 / best / 1e6);
   }
+  printf("car geometry (380 entries per sample):\n");
+  for (int tile : {16, 32, 64})
+    for (int bps : {1, 2}) {
+      float best = 1e9f;
+      for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(a);
+        probe_car<<<148 * bps, 12 * 32>>>(d, M, tile);
+        cudaEventRecord(b); cudaEventSynchronize(b);
+        float ms; cudaEventElapsedTime(&ms, a, b);
+        if (rep && ms < best) best = ms;
+      }
+      printf("  tile %3d  warps/SM %3d  %8.0f GB/s  (%.3f ms)\n", tile, 12 * bps, 380.0 * M * 8 / best / 1e6, best);
+    }
   return cudaDeviceSynchronize() != cudaSuccess;
 }
