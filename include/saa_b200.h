@@ -248,6 +248,32 @@ int saa_hopper_friction(saa_handle *h, int32_t n_c, const double *px_host,
                         void *mu_dev, void *dmu_dev, const double *lambda_dev,
                         double *hess_sums_dev, void *stream);
 
+/* ---- tail-reduced subproblem (no reference counterpart) ----
+ * At the solution of the Rockafellar-Uryasev program (drone/drone_risk.py:327-368,
+ * car/driving.py:331-372) only the samples in the upper alpha-tail of
+ * Z_i = max g_i have y_i > 0, so the host QP solver can be fed the K samples with
+ * the largest Z_i at the current iterate instead of all M: a handle created with
+ * M_local = K, M_global = M (the CVaR row keeps M*alpha*t, the expectation rows
+ * keep the mean over all M samples) and output geometry (K, 0).  Per iteration:
+ *   saa_linearize_means (full handle)  -> mean sums over ALL samples and Z_i, no matrix
+ *   saa_select_tail     (full handle)  -> indices of the K largest Z_i, ascending
+ *   saa_gather_samples  (K handle)     -> packed samples of those indices
+ *   saa_linearize_assemble(K handle, finalize = 0) + saa_finalize_means(K handle, full sums)
+ * The result equals the full matrix with the other samples' rows and y columns deleted. */
+/* Sample-mean sums (layout of saa_linearize_assemble's mean_sums_dev) and, if Z_dev
+ * is not NULL, Z_i = max_{o,k} g_i[o,k] of every local sample, without assembling.  */
+int saa_linearize_means(saa_handle *h, const double *us_host, void *Z_dev,
+                        double *mean_sums_dev, void *stream);
+/* idx_out_dev[0..K): indices (ascending) of the K largest of the M_local values
+ * Z_dev (handle precision); ties at the threshold go to the smaller index.
+ * Exact and deterministic (radix select + ordered compaction).                  */
+int saa_select_tail(saa_handle *h, const void *Z_dev, int64_t K,
+                    int64_t *idx_out_dev, void *stream);
+/* dst's M_local samples := samples idx_dev[0..dst.M_local) of src (packed inputs
+ * are copied device to device; dst needs saa_set_params_* but no saa_set_samples_*). */
+int saa_gather_samples(saa_handle *dst, const saa_handle *src,
+                       const int64_t *idx_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -81,6 +81,9 @@ _PROTOTYPES = {
                                          C.c_void_p, C.c_void_p]),
     "saa_hopper_friction": (C.c_int, [_H, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p]),
+    "saa_linearize_means": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "saa_select_tail": (C.c_int, [_H, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "saa_gather_samples": (C.c_int, [_H, _H, C.c_void_p, C.c_void_p]),
 }
 EXPORTS = tuple(_PROTOTYPES)
 

@@ -137,6 +137,13 @@ class Model:
             print("slack_var =", self.res.x[-2])
         return us_sol, t_risk_sol
 
+    # -- tail-reduced subproblem (no reference counterpart; riskaversetrajopt_b200/tail.py) ----
+    def tail_subproblem(self, K=None, margin=0.25):
+        """-> ``TailSubproblem``: the QP restricted to the K samples with the largest constraint
+        values at the iterate (default K = ceil((1 + margin) alpha M)), selected on the device."""
+        from ..tail import TailSubproblem
+        return TailSubproblem(self.path, K=K, margin=margin)
+
     # -- Monte-Carlo verification (reference :630-638, :670) -------------------------------
     def monte_carlo_constraints(self, us_mat):
         Z, _ = self.path.cvar_terms(us_mat, 0.0, 1e-6)

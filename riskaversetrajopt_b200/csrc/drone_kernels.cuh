@@ -14,7 +14,7 @@
 //
 // Thread mapping: one warp owns a tile of 16 samples; lanes 0-15 run the x axis
 // of those samples, lanes 16-31 the y axis (the z axis only feeds the sample-mean
-// rows: drone_zmean_kernel).  For each control step j the lane runs the
+// rows: drone_axis_mean_kernel).  For each control step j the lane runs the
 // sensitivity chain k = j+1..S in registers and stages the 3*(S-1-j) CSC entries
 // of its sample for column (j, axis) in shared memory; the warp then streams the
 // two column sub-runs (16 samples x 3*(S-1-j) contiguous doubles each) to global
@@ -356,14 +356,16 @@ drone_assemble_kernel(const __grid_constant__ DroneArgs<T, S> A) {
   }
 }
 
-// ---- z-axis rows of the sample mean (separate, tiny kernel) ---------------------------
+// ---- sample-mean rows of ONE axis (separate, tiny kernel) ------------------------------
 // The z axis never enters the planar obstacle rows; it only contributes d x_S^z / d u^z and the
-// z linearisation offsets to the sample-mean rows.  One thread per sample: rollout, then one
-// adjoint sweep carrying e_p and e_v; the 2S+1 sums stay in registers over the thread's samples
-// and are reduced once at the end.  Reads 8 + 8S bytes per sample.
+// z linearisation offsets to the sample-mean rows, so the assemble launch runs this kernel with
+// axis = 2.  The means-only pass (saa_linearize_means: expectation rows and Z_i without the
+// matrix, for the tail-reduced subproblem) runs it for all three axes.  One thread per sample:
+// rollout, then one adjoint sweep carrying e_p and e_v; the 2S+1 sums stay in registers over the
+// thread's samples and are reduced once at the end.  Reads 8 + 8S bytes per sample.
 template <typename T, int S, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
-drone_zmean_kernel(const __grid_constant__ DroneArgs<T, S> A, double *__restrict__ partials) {
+drone_axis_mean_kernel(const __grid_constant__ DroneArgs<T, S> A, int axis, double *__restrict__ partials) {
   using Rd = DroneRed<S>;
   __shared__ double red[WARPS][2 * S + 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -373,20 +375,24 @@ drone_zmean_kernel(const __grid_constant__ DroneArgs<T, S> A, double *__restrict
 #pragma unroll
   for (int j = 0; j < S; ++j) accv[j] = 0.0;
   const T dt = A.dt, c2 = T(2) * A.drag;
+  const T p0 = A.x0[axis], v0 = A.x0[3 + axis], pf = A.xf[axis], vf = A.xf[3 + axis];
+  T ua[S];
+#pragma unroll
+  for (int k = 0; k < S; ++k) ua[k] = A.us[k * 3 + axis];
   for (i64 s = (i64)blockIdx.x * blockDim.x + threadIdx.x; s < A.M; s += (i64)gridDim.x * blockDim.x) {
     T dwz[S];
 #pragma unroll
-    for (int k = 0; k < S; ++k) dwz[k] = __ldcs(A.dw + (i64)(k * 3 + 2) * A.Mpad + s);
+    for (int k = 0; k < S; ++k) dwz[k] = __ldcs(A.dw + (i64)(k * 3 + axis) * A.Mpad + s);
     const T inv_m = T(1) / __ldcs(A.mass + s);
     const T dtm = dt * inv_m, a21 = -A.kp * dtm, nz = A.noise_c * inv_m;
     T a22z[S];
-    T p = A.x0[2], v = A.x0[5], tp = T(0), tv = T(0);
+    T p = p0, v = v0, tp = T(0), tv = T(0);
 #pragma unroll
     for (int k = 0; k < S; ++k) {
       const T absv = fabs(v);
       const T a22 = T(1) - dtm * (A.kd + c2 * absv);
       a22z[k] = a22;
-      const T u = A.us[k * 3 + 2];
+      const T u = ua[k];
       const T acc = (u - A.kp * p - A.kd * v - A.drag * absv * v) * inv_m;
       const T ntp = fma(dt, tv, tp);
       const T ntv = fma(a22, tv, fma(a21, tp, dtm * u));
@@ -394,8 +400,8 @@ drone_zmean_kernel(const __grid_constant__ DroneArgs<T, S> A, double *__restrict
       v = v + dt * acc + nz * dwz[k];
       p = np_; tp = ntp; tv = ntv;
     }
-    valp += (double)(-(p - A.xf[2]) + tp);      // linearisation offsets (:271)
-    valv += (double)(-(v - A.xf[5]) + tv);
+    valp += (double)(-(p - pf) + tp);      // linearisation offsets (:271)
+    valv += (double)(-(v - vf) + tv);
     T pp = T(1), pv = T(0), vp = T(0), vv = T(1);   // adjoints of p_S (pp, pv) and v_S (vp, vv)
 #pragma unroll
     for (int j = S - 1; j >= 0; --j) {
@@ -413,14 +419,14 @@ drone_zmean_kernel(const __grid_constant__ DroneArgs<T, S> A, double *__restrict
   { const double r = sum32(valp); if (lane == 0) red[warp][2 * S - 1] = r; }
   { const double r = sum32(valv); if (lane == 0) red[warp][2 * S] = r; }
   __syncthreads();
-  // one full row of partials per block: zeros except the z slots
+  // one full row of partials per block: zeros except this axis' slots
   double *row = partials + (i64)blockIdx.x * Rd::N;
   for (int r = threadIdx.x; r < Rd::N; r += WARPS * 32) {
     int src = -1;
-    if (r >= Rd::FIN_P + 2 * (S - 1) && r < Rd::FIN_P + 3 * (S - 1)) src = r - (Rd::FIN_P + 2 * (S - 1));
-    else if (r >= Rd::FIN_V + 2 * S && r < Rd::FIN_V + 3 * S) src = S - 1 + r - (Rd::FIN_V + 2 * S);
-    else if (r == Rd::VAL + 2) src = 2 * S - 1;
-    else if (r == Rd::VAL + 5) src = 2 * S;
+    if (r >= Rd::FIN_P + axis * (S - 1) && r < Rd::FIN_P + (axis + 1) * (S - 1)) src = r - (Rd::FIN_P + axis * (S - 1));
+    else if (r >= Rd::FIN_V + axis * S && r < Rd::FIN_V + (axis + 1) * S) src = S - 1 + r - (Rd::FIN_V + axis * S);
+    else if (r == Rd::VAL + axis) src = 2 * S - 1;
+    else if (r == Rd::VAL + 3 + axis) src = 2 * S;
     double acc = 0.0;
     if (src >= 0)
       for (int w = 0; w < WARPS; ++w) acc += red[w][src];

@@ -10,6 +10,7 @@
 #include "drone_kernels.cuh"
 #include "car_kernels.cuh"
 #include "hopper_kernels.cuh"
+#include "tail_kernels.cuh"
 
 using namespace saa;
 
@@ -303,7 +304,7 @@ int launch_drone_assemble(saa_handle *h, const double *us, int scp_iter, void *A
   kern<<<grid, kWarps * 32, sizeof(Smem), st>>>(A);
   SAA_CUDA(h, cudaGetLastError());
   if (MODE == DRONE_EXPAND) return SAA_OK;
-  drone_zmean_kernel<T, kS, kZWarps><<<gridz, kZWarps * 32, 0, st>>>(A, h->d_partials + (i64)grid * DroneRed<kS>::N);
+  drone_axis_mean_kernel<T, kS, kZWarps><<<gridz, kZWarps * 32, 0, st>>>(A, 2, h->d_partials + (i64)grid * DroneRed<kS>::N);
   SAA_CUDA(h, cudaGetLastError());
   const int n = DroneRed<kS>::N;
   reduce_partials_kernel<double><<<(n + 3) / 4, 128, 0, st>>>(h->d_partials, grid + gridz, n, sums);
@@ -402,6 +403,7 @@ int launch_merge(saa_handle *h, const void *sAx, const void *su, i64 M_shard, i6
 
 #include "car_host.cuh"
 #include "hopper_host.cuh"
+#include "tail_host.cuh"
 
 // =============================================================================
 // C ABI

@@ -61,6 +61,7 @@ class DevicePath:
         self._bufs = {}          # relaxed_pattern -> dict(Ax, l, u, const_state)
         self._pinned = {}
         self._keep = []          # sample tensors stay alive until the pack kernel ran
+        self._params_call = None # (method name, args) of the last set_params_* call (tail.py replays it)
         self.mean_len = int(lib.saa_mean_len(self._h))
         self.mean_sums = torch.zeros(max(self.mean_len, 1), dtype=torch.float64, device=self.device)
 
@@ -105,6 +106,7 @@ class DevicePath:
                 s.obs_positions[o][d] = float(p.obs_positions[o][d])
         s.osqp_tol = float(osqp_tol)
         check(lib.saa_set_params_drone(self._h, C.byref(s)), self._h)
+        self._params_call = ('set_params_drone', (p, osqp_tol))
 
     def set_params_car(self, p, beta, osqp_tol):
         s = _lib.CarParams()
@@ -114,6 +116,7 @@ class DevicePath:
         s.goal[:] = [float(v) for v in np.concatenate([p.position_ego_goal, p.velocity_ego_goal])]
         s.osqp_tol = float(osqp_tol)
         check(lib.saa_set_params_car(self._h, C.byref(s)), self._h)
+        self._params_call = ('set_params_car', (p, beta, osqp_tol))
 
     def set_samples_drone(self, masses, DWs, obs_Qs):
         Q = obs_Qs if torch.is_tensor(obs_Qs) else np.asarray(obs_Qs)

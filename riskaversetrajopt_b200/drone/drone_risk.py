@@ -130,6 +130,13 @@ class Model:
             print("slack_var =", self.res.x[-2])
         return us_sol, t_risk_sol
 
+    # -- tail-reduced subproblem (no reference counterpart; riskaversetrajopt_b200/tail.py) ----
+    def tail_subproblem(self, K=None, margin=0.25):
+        """-> ``TailSubproblem``: the QP restricted to the K samples with the largest constraint
+        values at the iterate (default K = ceil((1 + margin) alpha M)), selected on the device."""
+        from ..tail import TailSubproblem
+        return TailSubproblem(self.path, K=K, margin=margin)
+
     # -- Monte-Carlo verification (reference drone_risk.py:656-662, :694) -------------
     def monte_carlo_constraints(self, us_mat):
         """-> (B_satisfied (M,) bool, max_constraint (M,)) as the vmapped
