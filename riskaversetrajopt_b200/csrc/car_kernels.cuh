@@ -67,12 +67,12 @@ __device__ __forceinline__ void sincos_core(double x, double *s, double *c) {
   ps = fma(z, ps, K[8]);
   ps = fma(z, ps, K[9]);
   const double sn = fma(r * z, ps, r);
-  double pc = fma(z, K[10], K[11]);
+  double pc = fma(z, K[1]0, K[1]1);
   pc = fma(z, pc, K[12]);
   pc = fma(z, pc, K[13]);
   pc = fma(z, pc, K[14]);
   pc = fma(z, pc, K[15]);
-  const double cs = fma(z * z, pc, fma(z, K[16], 1.0));
+  const double cs = fma(z * z, pc, fma(z, K[1]6, 1.0));
   // n mod 4: 0 (s, c)  1 (c, -s)  2 (-s, -c)  3 (-c, s)
   const bool swap = n & 1;
   double so = swap ? cs : sn, co = swap ? sn : cs;
@@ -81,16 +81,41 @@ __device__ __forceinline__ void sincos_core(double x, double *s, double *c) {
   co = __hiloint2double(__double2hiint(co) ^ cflip, __double2loint(co));
   *s = so; *c = co;
 }
-__device__ __forceinline__ void sincos_core(float x, float *s, float *c) { sincosf(x, s, c); }
-// true if the core's reduction does not cover x (|x| >= 1e5, NaN, Inf)
+// FP32 counterpart (|x| < 1e4): same scheme with the 1.5 2^23 shift, pi/2 split in three floats,
+// cephes sinf / cosf kernels (about 1 ulp in float)
+__device__ __forceinline__ void sincos_core(float x, float *s, float *c) {
+  const float SHIFT = 12582912.0f;                            // 1.5 * 2^23
+  const float t = fmaf(x, 0.636619747f, SHIFT);
+  const int n = __float_as_int(t);                            // low mantissa bits = n (mod 4 is all we need)
+  const float nf = t - SHIFT;
+  float r = fmaf(nf, -1.57079637e+00f, x);
+  r = fmaf(nf, 4.37113883e-08f, r);
+  r = fmaf(nf, 1.71512451e-15f, r);
+  const float z = r * r;
+  float ps = fmaf(z, -1.9515295891e-4f, 8.3321608736e-3f);
+  ps = fmaf(z, ps, -1.6666654611e-1f);
+  const float sn = fmaf(r * z, ps, r);
+  float pc = fmaf(z, 2.443315711809948e-5f, -1.388731625493765e-3f);
+  pc = fmaf(z, pc, 4.166664568298827e-2f);
+  const float cs = fmaf(z * z, pc, fmaf(z, -0.5f, 1.0f));
+  const bool swap = n & 1;
+  float so = swap ? cs : sn, co = swap ? sn : cs;
+  so = __int_as_float(__float_as_int(so) ^ ((n & 2) << 30));
+  co = __int_as_float(__float_as_int(co) ^ (((n + 1) & 2) << 30));
+  *s = so; *c = co;
+}
+// true if the core's reduction does not cover x (|x| >= 1e5 in FP64, 1e4 in FP32, NaN, Inf)
 __device__ __forceinline__ bool sincos_big(double x) { return (__double2hiint(x) & 0x7fffffff) >= 0x40f86a00; }
-__device__ __forceinline__ bool sincos_big(float) { return false; }
+__device__ __forceinline__ bool sincos_big(float x) { return (__float_as_int(x) & 0x7fffffff) >= 0x461c4000; }
 
 __device__ __forceinline__ void sincos_fast(double x, double *s, double *c) {
   if (sincos_big(x)) sincos(x, s, c);      // library slow path
   else sincos_core(x, s, c);
 }
-__device__ __forceinline__ void sincos_fast(float x, float *s, float *c) { sincosf(x, s, c); }
+__device__ __forceinline__ void sincos_fast(float x, float *s, float *c) {
+  if (sincos_big(x)) sincosf(x, s, c);
+  else sincos_core(x, s, c);
+}
 
 template <int S> struct CarRed {
   static constexpr int PX = 0;                    // + c*(S-1) + j    (c<2, j<S-1)
