@@ -67,12 +67,12 @@ __device__ __forceinline__ void sincos_core(double x, double *s, double *c) {
   ps = fma(z, ps, K[8]);
   ps = fma(z, ps, K[9]);
   const double sn = fma(r * z, ps, r);
-  double pc = fma(z, K[1]0, K[1]1);
+  double pc = fma(z, K[10], K[11]);
   pc = fma(z, pc, K[12]);
   pc = fma(z, pc, K[13]);
   pc = fma(z, pc, K[14]);
   pc = fma(z, pc, K[15]);
-  const double cs = fma(z * z, pc, fma(z, K[1]6, 1.0));
+  const double cs = fma(z * z, pc, fma(z, K[16], 1.0));
   // n mod 4: 0 (s, c)  1 (c, -s)  2 (-s, -c)  3 (-c, s)
   const bool swap = n & 1;
   double so = swap ? cs : sn, co = swap ? sn : cs;
