@@ -95,3 +95,62 @@ def test_drone_million_samples_properties():
     keep = Ax[:1140 * M + 177].clone()
     path.assemble(us, 2, Z=Z)
     assert torch.equal(keep, Ax[:1140 * M + 177])
+
+
+def _car_col(j, c, M):
+    """start of sample 0's run of u column (j, c) of the car matrix, run length (CarCol)."""
+    L = S - 1 - j
+    return (8 * j + 3 + 4 * c) + M * (2 * j * (S - 1) - j * (j - 1) + c * L), L
+
+
+def test_car_million_samples_properties():
+    import torch
+    if torch.cuda.get_device_properties(0).total_memory < 60e9:
+        pytest.skip("needs ~12 GB of device memory")
+    from oracle.oracle_b import CarOracleB
+    from riskaversetrajopt_b200.car.driving import Model, sample_uncertain_parameters
+    M = 1_000_000
+    np.random.seed(4)
+    samples = sample_uncertain_parameters(M, 'saa')        # host RNG in the reference's order (~1.4 GB)
+    model = Model(M, 'saa', 0.05, samples=samples)
+    path = model.path
+    dev = path.device
+    us = model.initial_guess_us_mat() + 0.1 * np.random.RandomState(0).randn(S, 2)
+    Z = torch.empty(M, dtype=torch.float64, device=dev)
+    b = path.assemble(us, 2, Z=Z)
+    Ax, u = b['Ax'], b['u']
+    row_s0 = 4 + 1 + M
+    # sampled samples against the oracle (generic dense 8x8 recursion)
+    idx = np.unique(np.concatenate([[0, 1, 15, 16, M - 1, M - 17], np.random.RandomState(1).randint(0, M, 42)]))
+    it = torch.as_tensor(idx, device=dev)
+    ref = CarOracleB(*(a[idx] for a in samples), 'saa', 0.05)
+    _, _, _, g_du, g_up, _ = ref.per_sample(us)
+    rel = lambda a, w: float(np.max(np.abs(a - w) / np.maximum(np.abs(w), 1e-12)))
+    ub = u[row_s0 + it[:, None] * S + torch.arange(S, device=dev)[None, :]].cpu().numpy()
+    assert rel(ub, g_up) < 1e-9
+    for j in range(S - 1):
+        for c in (0, 1):
+            start, L = _car_col(j, c, M)
+            got = Ax[start + it[:, None] * L + torch.arange(L, device=dev)[None, :]].cpu().numpy()
+            assert rel(got, g_du[:, j + 1:, j * 2 + c]) < 1e-9, (j, c)
+    # tail-reduced matrix == full matrix restricted, bitwise
+    tail = model.tail_subproblem(margin=0.25)
+    K = tail.K
+    br = tail.assemble(us, 2)
+    sel, ar = tail.idx, torch.arange(K, device=dev)
+    order = torch.sort(Z, descending=True, stable=True).indices
+    assert torch.equal(torch.sort(order[:K]).values, sel)
+    for j in range(S - 1):
+        for c in (0, 1):
+            sf, L = _car_col(j, c, M)
+            sr, _ = _car_col(j, c, K)
+            e = torch.arange(L, device=dev)[None, :]
+            assert torch.equal(br['Ax'][sr + ar[:, None] * L + e], Ax[sf + sel[:, None] * L + e]), (j, c)
+    e = torch.arange(S, device=dev)[None, :]
+    assert torch.equal(br['u'][4 + 1 + K + ar[:, None] * S + e], u[row_s0 + sel[:, None] * S + e])
+    assert torch.equal(br['l'][:4], b['l'][:4]) and torch.equal(br['u'][:4], b['u'][:4])
+    # kernels agree with each other
+    from riskaversetrajopt_b200.car import driving_params as cp
+    Zc, out3 = path.cvar_terms(us, t_risk=-1.0, sat_tol=1e-6)
+    assert torch.allclose(Z - cp.OSQP_TOL, Zc, rtol=0, atol=1e-14)
+    assert out3[2].item() == Zc.max().item()
