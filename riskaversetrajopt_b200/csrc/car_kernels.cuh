@@ -104,6 +104,53 @@ __device__ __forceinline__ void sincos_core(float x, float *s, float *c) {
   co = __int_as_float(__float_as_int(co) ^ (((n + 1) & 2) << 30));
   *s = so; *c = co;
 }
+// N independent evaluations written stage by stage (source order alternates between them; ptxas
+// is free to re-serialise, and does so in FP64)
+template <int N>
+__device__ __forceinline__ void sincos_core_n(const double (&x)[N], double (&s)[N], double (&c)[N]) {
+  const double *K = kSinCosC;
+  const double SHIFT = 6755399441055744.0;
+  double t[N], nf[N], r[N], z[N], ps[N], pc[N], sn[N], cs[N];
+  int n[N];
+#pragma unroll
+  for (int q = 0; q < N; ++q) t[q] = fma(x[q], K[0], SHIFT);
+#pragma unroll
+  for (int q = 0; q < N; ++q) { n[q] = __double2loint(t[q]); nf[q] = t[q] - SHIFT; }
+#pragma unroll
+  for (int q = 0; q < N; ++q) r[q] = fma(nf[q], K[1], x[q]);
+#pragma unroll
+  for (int q = 0; q < N; ++q) r[q] = fma(nf[q], K[2], r[q]);
+#pragma unroll
+  for (int q = 0; q < N; ++q) r[q] = fma(nf[q], K[3], r[q]);
+#pragma unroll
+  for (int q = 0; q < N; ++q) z[q] = r[q] * r[q];
+#pragma unroll
+  for (int q = 0; q < N; ++q) { ps[q] = fma(z[q], K[4], K[5]); pc[q] = fma(z[q], K[10], K[11]); }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+#pragma unroll
+    for (int q = 0; q < N; ++q) { ps[q] = fma(z[q], ps[q], K[6 + i]); pc[q] = fma(z[q], pc[q], K[12 + i]); }
+  }
+#pragma unroll
+  for (int q = 0; q < N; ++q) {
+    sn[q] = fma(r[q] * z[q], ps[q], r[q]);
+    cs[q] = fma(z[q] * z[q], pc[q], fma(z[q], K[16], 1.0));
+  }
+#pragma unroll
+  for (int q = 0; q < N; ++q) {
+    const bool swap = n[q] & 1;
+    double so = swap ? cs[q] : sn[q], co = swap ? sn[q] : cs[q];
+    so = __hiloint2double(__double2hiint(so) ^ ((n[q] & 2) << 30), __double2loint(so));
+    co = __hiloint2double(__double2hiint(co) ^ (((n[q] + 1) & 2) << 30), __double2loint(co));
+    s[q] = so; c[q] = co;
+  }
+}
+template <int N>
+__device__ __forceinline__ void sincos_core_n(const float (&x)[N], float (&s)[N], float (&c)[N]) {
+#pragma unroll
+  for (int q = 0; q < N; ++q) sincos_core(x[q], &s[q], &c[q]);
+}
+
 // true if the core's reduction does not cover x (|x| >= 1e5 in FP64, 1e4 in FP32, NaN, Inf)
 __device__ __forceinline__ bool sincos_big(double x) { return (__double2hiint(x) & 0x7fffffff) >= 0x40f86a00; }
 __device__ __forceinline__ bool sincos_big(float x) { return (__float_as_int(x) & 0x7fffffff) >= 0x461c4000; }

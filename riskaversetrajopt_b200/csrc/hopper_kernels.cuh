@@ -45,13 +45,31 @@ template <typename T> struct __align__(4 * sizeof(T)) HopperFeat { T I, th, ta, 
 
 template <typename T, bool HESS, bool BIG>
 __device__ __forceinline__ void hopper_element(const HopperFeat<T> *row, int F, T p, T &m0, T &m1, T &m2) {
+  int f = 0;
+  if (!BIG && sizeof(T) == 4) {
+    // FP32: two features per iteration in one straight-line block (0.93 -> 0.77 ms); in FP64 ptxas
+    // serialises the two evaluations again and the plain loop below is as fast
+#pragma unroll 1
+    for (; f + 2 <= F; f += 2) {
+      const HopperFeat<T> f0 = row[f], f1 = row[f + 1];
+      const T x[2] = {fma(f0.th, p, f0.ta), fma(f1.th, p, f1.ta)};
+      T sn[2], cs[2];
+      sincos_core_n<2>(x, sn, cs);
+      m0 = fma(f0.I, cs[0], m0);
+      m1 = fma(f0.nit, sn[0], m1);
+      if (HESS) m2 = fma(f0.nit * f0.th, cs[0], m2);
+      m0 = fma(f1.I, cs[1], m0);
+      m1 = fma(f1.nit, sn[1], m1);
+      if (HESS) m2 = fma(f1.nit * f1.th, cs[1], m2);
+    }
+  }
 #pragma unroll 2
-  for (int f = 0; f < F; ++f) {
+  for (; f < F; ++f) {
     const HopperFeat<T> ft = row[f];
     const T x = fma(ft.th, p, ft.ta);
     T sn, cs;
     if (BIG) sincos_t(x, &sn, &cs);      // library routine (any argument)
-    else sincos_core(x, &sn, &cs);       // branch free: consecutive features interleave
+    else sincos_core(x, &sn, &cs);       // branch free
     m0 = fma(ft.I, cs, m0);
     m1 = fma(ft.nit, sn, m1);
     if (HESS) m2 = fma(ft.nit * ft.th, cs, m2);
