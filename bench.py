@@ -167,7 +167,7 @@ def bench_us():
 
 
 # --------------------------------------------------------------------------- CPU legs
-def cpu_port_baseline(M_s=None, budget_s=20.0):
+def cpu_port_baseline(M_s=None, budget_s=12.0):
     """Oracle port (analytic restatement) on the host cores over a bounded sample."""
     from oracle import cpu_port
     return cpu_port.time_drone(bench_us(), budget_s=budget_s, M_s=M_s)
