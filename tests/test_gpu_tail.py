@@ -166,3 +166,34 @@ def test_reduced_qp_has_the_full_qp_solution(drone_seed0):
     assert np.allclose(xr[60:60 + tail.K], xf[60 + idx], atol=2e-5)
     # ... which the a-posteriori check of the reduced solve confirms on the device
     assert tail.left_out_margin(xr[-1]) <= 0.0
+
+
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+def test_tail_edge_sizes_and_fp32(precision):
+    """K = M reproduces the full matrix; K = 1 keeps the worst sample; FP32 handles select on FP32 keys."""
+    from riskaversetrajopt_b200.drone import drone_params as dp
+    from riskaversetrajopt_b200.drone.drone_utils import sample_uncertain_parameters
+    from riskaversetrajopt_b200.drone.drone_risk import Model
+    np.random.seed(9)
+    M = 77
+    DWs, masses, obs_Qs = sample_uncertain_parameters('saa', M=M)
+    model = Model(dp.S, DWs, masses, obs_Qs, 'saa', 0.1, precision=precision)
+    us = model.initial_guess_us_mat() + 0.05 * np.random.RandomState(3).randn(dp.S, dp.n_u)
+    A, l, u = model.get_constraints_coeffs(us, 2)
+    _, Zmax = model.monte_carlo_constraints(us)
+    tol = dict(rtol=1e-12, atol=1e-15) if precision == "fp64" else dict(rtol=1e-5, atol=1e-7)
+    for K in (M, 1, 16, 17):
+        tail = model.tail_subproblem(K=K)
+        Ar, lr, ur, idx = tail.get_constraints_coeffs(us, 2)
+        assert np.array_equal(idx, _select_ref(Zmax, K))
+        As, ls, us_ = _submatrix(A, l, u, idx, M, 60, 60, 6)
+        assert np.array_equal(Ar.indptr, As.indptr) and np.array_equal(Ar.indices, As.indices)
+        fin = Ar.indices < 6
+        assert np.array_equal(Ar.data[~fin], As.data[~fin])
+        assert np.allclose(Ar.data[fin], As.data[fin], **tol)
+        assert np.array_equal(lr[6:], ls[6:]) and np.array_equal(ur[6:], us_[6:])
+    with pytest.raises(ValueError):
+        model.tail_subproblem(K=M + 1)
+    base = Model(dp.S, DWs, masses, obs_Qs, 'baseline', 0.1)
+    with pytest.raises(ValueError):
+        base.tail_subproblem()
