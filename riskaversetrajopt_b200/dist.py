@@ -19,6 +19,12 @@ Per SCP iteration:
        into the CSC entries with the same instructions a single GPU would use (drone only),
      * ``'nccl'``     – ``gather`` of the compact blocks to rank 0 followed by
        ``saa_merge_shard`` (device-to-device run copies).
+
+``ShardedTailAssembler`` delivers the tail-reduced subproblem (``tail.py``) instead: every rank
+keeps the ``K_r ~ (1 + margin) alpha M_r`` samples of ITS shard with the largest constraint
+values (a stratified selection: the shards are i.i.d., so the global alpha-tail is inside the union
+up to binomial fluctuations far below the margin; the a-posteriori check is the max over ranks of
+``left_out_margin``) and stores their rows straight into rank 0's K-sample matrix over NVLink.
 """
 import numpy as np
 import torch
@@ -231,3 +237,65 @@ class ShardedAssembler:
         if p.problem == _lib.SAA_DRONE:
             return 1140 * p.M_out + 177
         return 380 * p.M_out + 156
+
+
+class ShardedTailAssembler:
+    """Tail-reduced subproblem of a sharded sample set, assembled on rank 0 (peer stores).
+
+    ``path``: this rank's ``DevicePath`` over its shard (``M_local`` of ``M_global`` samples, params
+    and samples set).  Rank r contributes its ``K_r`` worst samples as samples
+    ``offset_r .. offset_r + K_r`` of a matrix for ``K_total = sum K_r`` samples; the CVaR row keeps
+    ``M_global alpha t`` and the expectation rows the mean over all ``M_global`` samples."""
+
+    def __init__(self, path, margin=0.25, K_local=None, group=None):
+        from .tail import TailSubproblem
+        self.path, self.group = path, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        K = int(min(path.M_local, max(1, int(np.ceil((1.0 + margin) * path.alpha * path.M_local))))
+                if K_local is None else K_local)
+        counts = [None] * self.world
+        dist.all_gather_object(counts, K, group=group)
+        self.counts = [int(c) for c in counts]
+        self.K_total, self.offset = sum(self.counts), sum(self.counts[:self.rank])
+        self.tail = TailSubproblem(path, K=K, out_geometry=(self.K_total, self.offset))
+        sub = self.tail.sub
+        n_rows, _, nnz = sub.pattern_sizes(False)
+        npdt = np.float64 if sub.bits == 64 else np.float32
+        self.shared = SharedBuffers([nnz, n_rows, n_rows], npdt, sub.device, 0, group)
+        bufs = self.shared.tensors if self.rank == 0 else self.shared.ptrs
+        self.out = dict(Ax=bufs[0], l=bufs[1], u=bufs[2], const_state=None)
+        kmax = max(self.counts)                                  # all_gather wants equal sizes: pad
+        self._idx_send = torch.zeros(kmax, dtype=torch.int64, device=sub.device)
+        self._idx_all = [torch.empty(kmax, dtype=torch.int64, device=sub.device) for _ in self.counts]
+
+    def pattern(self):
+        """(n_rows, n_cols, indptr, indices) of the K_total-sample matrix (rank 0's result)."""
+        return self.tail.sub.pattern(False)
+
+    def step(self, us_mat, scp_iter):
+        """One SCP iteration.  Rank 0 gets (dict(Ax, l, u) of device tensors, idx: the selected
+        samples' GLOBAL indices in the order of the matrix's sample blocks); other ranks (None, None)."""
+        p, t = self.path, self.tail
+        if scp_iter < p.relax_threshold() and p._uses_relaxed_pattern(scp_iter):
+            raise ValueError("the sharded tail gather covers scp_iter >= 1 for the car")
+        nccl = dist.get_backend(self.group) == 'nccl'
+        us = broadcast_controls(us_mat, 0, self.group, device=p.device if nccl else None)
+        b = t.assemble(us, scp_iter, out=self.out, write_shared=(self.rank == 0), finalize=False)
+        all_reduce_sums(p.mean_sums, self.group)                 # sums over ALL samples of all ranks
+        self._idx_send[:t.K] = t.idx + p.sample_offset
+        dist.all_gather(self._idx_all, self._idx_send, group=self.group)
+        torch.cuda.current_stream(p.device).synchronize()
+        dist.barrier(group=self.group)                           # remote rows have landed in rank 0's HBM
+        if self.rank != 0:
+            return None, None
+        t.finalize_means(b, scp_iter)
+        return b, torch.cat([v[:c] for v, c in zip(self._idx_all, self.counts)])
+
+    def left_out_margin(self, t_risk):
+        """max over all ranks of ``TailSubproblem.left_out_margin``."""
+        v = torch.tensor([self.tail.left_out_margin(t_risk)], dtype=torch.float64, device=self.path.device)
+        dist.all_reduce(v, op=dist.ReduceOp.MAX, group=self.group)
+        return float(v.item())
+
+    def close(self):
+        self.shared.close()

@@ -29,13 +29,16 @@ from .device_path import DevicePath, _TORCH_DT
 
 
 class TailSubproblem:
-    def __init__(self, path, K=None, margin=0.25):
-        """``path``: the ``DevicePath`` of a drone / car ``Model`` (method 'saa', all samples on
-        this GPU).  ``K`` samples are kept (default ``ceil((1 + margin) * alpha * M)``)."""
+    def __init__(self, path, K=None, margin=0.25, out_geometry=None):
+        """``path``: the ``DevicePath`` of a drone / car ``Model`` (method 'saa').  ``K`` of its
+        local samples are kept (default ``ceil((1 + margin) * alpha * M_local)``).
+        ``out_geometry = (K_total, first)`` places them as samples ``first .. first + K`` of a
+        matrix for ``K_total`` samples (multi-GPU: ``dist.ShardedTailAssembler``); by default the
+        matrix holds exactly these K samples, which requires all samples to be on this GPU."""
         if path.method != 'saa':
             raise ValueError("the tail reduction applies to the CVaR ('saa') program")
-        if path.M_local != path.M_global:
-            raise ValueError("the tail reduction selects among the samples of one GPU")
+        if out_geometry is None and path.M_local != path.M_global:
+            raise ValueError("the samples are sharded: use dist.ShardedTailAssembler")
         if path._params_call is None:
             raise ValueError("set the parameters and samples of the full path first")
         self.full = path
@@ -43,10 +46,10 @@ class TailSubproblem:
         self.K = int(min(M, max(1, math.ceil((1.0 + margin) * path.alpha * M))) if K is None else K)
         if not 1 <= self.K <= M:
             raise ValueError("need 1 <= K <= M")
-        self.sub = DevicePath(path.problem, path.method, path.S, path.alpha, self.K, M_global=M,
+        self.sub = DevicePath(path.problem, path.method, path.S, path.alpha, self.K, M_global=path.M_global,
                               sample_offset=0, variant=path.variant,
                               precision={64: 'fp64', 32: 'fp32'}[path.bits], device=path.device.index)
-        self.sub.set_output_geometry(self.K, 0)
+        self.sub.set_output_geometry(*(out_geometry if out_geometry is not None else (self.K, 0)))
         name, args = path._params_call
         getattr(self.sub, name)(*args)
         dev = path.device
@@ -54,20 +57,35 @@ class TailSubproblem:
         self.idx = torch.empty(self.K, dtype=torch.int64, device=dev)
 
     # -- device side ------------------------------------------------------------------
-    def assemble(self, us_mat, scp_iter):
-        """-> dict of device buffers {Ax, l, u} of the K-sample matrix; ``self.idx`` holds the
-        selected sample indices (ascending), ``self.Z`` the Z_i of all samples."""
+    def select(self, us_mat):
+        """Means + Z_i of all local samples (``full.mean_sums``, ``self.Z``), the K largest
+        (``self.idx``, ascending) and their packed inputs into the K-sample handle."""
         f, s = self.full, self.sub
         us = f._us(us_mat)
         st = f._stream()
         check(lib.saa_linearize_means(f._h, us.ctypes.data, self.Z.data_ptr(), f.mean_sums.data_ptr(), st), f._h)
         check(lib.saa_select_tail(f._h, self.Z.data_ptr(), self.K, self.idx.data_ptr(), st), f._h)
         check(lib.saa_gather_samples(s._h, f._h, self.idx.data_ptr(), st), s._h)
-        b = s.assemble(us, scp_iter, finalize=False)
-        # expectation rows: mean over ALL samples (the K-sample sums of the launch above are dropped)
-        check(lib.saa_finalize_means(s._h, f.mean_sums.data_ptr(), int(scp_iter), b['Ax'].data_ptr(),
-                                     b['l'].data_ptr(), b['u'].data_ptr(), st), s._h)
+        return us
+
+    def assemble(self, us_mat, scp_iter, out=None, write_shared=True, finalize=True):
+        """-> dict of device buffers {Ax, l, u} of the K-sample matrix; ``self.idx`` holds the
+        selected sample indices (ascending), ``self.Z`` the Z_i of all samples.  ``out`` /
+        ``write_shared`` as in ``DevicePath.assemble``; with ``finalize=False`` the expectation
+        rows are left to the caller (``finalize_means`` after the all-reduce of ``full.mean_sums``)."""
+        us = self.select(us_mat)
+        b = self.sub.assemble(us, scp_iter, finalize=False, write_shared=write_shared, out=out)
+        if finalize:
+            self.finalize_means(b, scp_iter)
         return b
+
+    def finalize_means(self, b, scp_iter):
+        """Expectation rows = mean over ALL samples: the sums of the means pass over the full sample
+        set (all-reduced across ranks by the caller if sharded), not those of the K-sample launch."""
+        f, s = self.full, self.sub
+        ptr = lambda t: t.data_ptr() if torch.is_tensor(t) else int(t)
+        check(lib.saa_finalize_means(s._h, f.mean_sums.data_ptr(), int(scp_iter), ptr(b['Ax']),
+                                     ptr(b['l']), ptr(b['u']), f._stream()), s._h)
 
     # -- host side ----------------------------------------------------------------------
     def get_constraints_coeffs(self, us_mat, scp_iter, copy=True):

@@ -114,3 +114,99 @@ def test_two_ranks_reproduce_single_gpu(problem, M):
             row_s0_g, row_s0_s = nfin + 1 + M, nfin + 1 + cnt
             assert np.array_equal(su[row_s0_s:row_s0_s + cnt * R], u[row_s0_g + first * R:row_s0_g + (first + cnt) * R])
             assert np.allclose(su[:nfin], u[:nfin], rtol=1e-12, atol=1e-14)      # global means on every rank
+
+
+def _tail_worker(rank, world, initfile, M, problem, out):
+    import torch
+    import torch.distributed as dist
+    from riskaversetrajopt_b200 import _lib, dist as sd
+    from riskaversetrajopt_b200.device_path import DevicePath
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"file://{initfile}", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    rs = np.random.RandomState(0)
+    if problem == 'drone':
+        from riskaversetrajopt_b200.drone import drone_params as dp
+        from riskaversetrajopt_b200.drone.drone_utils import sample_uncertain_parameters
+        np.random.seed(0)
+        DWs, masses, obs_Qs = sample_uncertain_parameters('saa', M=M)
+        us, its, alpha = 0.1 * rs.randn(20, 3), (0, 2), 0.1
+
+        def make(first, cnt):
+            p = DevicePath(_lib.SAA_DRONE, 'saa', 20, alpha, cnt, M_global=M, sample_offset=first, device=rank)
+            p.set_params_drone(dp, dp.OSQP_TOL)
+            p.set_samples_drone(masses[first:first + cnt], DWs[first:first + cnt], obs_Qs[first:first + cnt])
+            return p
+    else:
+        from riskaversetrajopt_b200.car import driving_params as cp
+        from riskaversetrajopt_b200.car.driving import sample_uncertain_parameters, BETA
+        np.random.seed(0)
+        s = sample_uncertain_parameters(M, 'saa')
+        us, its, alpha = 0.01 + 0.3 * rs.randn(20, 2), (1, 2), 0.1
+
+        def make(first, cnt):
+            p = DevicePath(_lib.SAA_CAR, 'saa', 20, alpha, cnt, M_global=M, sample_offset=first, device=rank)
+            p.set_params_car(cp, BETA, cp.OSQP_TOL)
+            p.set_samples_car(*(x[first:first + cnt] for x in s))
+            return p
+    res = {}
+    first, cnt = sd.shard_range(M, world, rank)
+    asm = sd.ShardedTailAssembler(make(first, cnt), margin=0.5)
+    for it in its:
+        b, idx = asm.step(us if rank == 0 else np.zeros_like(us), it)
+        Zloc = asm.tail.Z.cpu().numpy()
+        sel = asm.tail.idx.cpu().numpy()
+        res[('local', it)] = (Zloc, sel, first)
+        if rank == 0:
+            res[('tail', it)] = tuple(b[k].cpu().numpy() for k in ('Ax', 'l', 'u')) + (idx.cpu().numpy(),)
+    res['margin'] = asm.left_out_margin(1e9)
+    if rank == 0:
+        res['pattern'] = asm.pattern()
+        single = make(0, M)
+        for it in its:
+            b = single.assemble(us, it)
+            res[('single', it)] = tuple(b[k].cpu().numpy() for k in ('Ax', 'l', 'u'))
+        res['single_pattern'] = single.pattern()
+    out[rank] = res
+    asm.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("problem,M", [("drone", 1000), ("car", 600), ("drone", 77)])
+def test_two_ranks_tail_subproblem(problem, M):
+    """Stratified tail selection on 2 ranks, rows stored into rank 0's K-sample matrix over NVLink:
+    the result is the single-GPU full matrix restricted to the selected samples."""
+    import scipy.sparse as sp
+    import torch
+    import torch.multiprocessing as mp
+    from test_gpu_tail import _select_ref, _submatrix
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    mgr = mp.Manager()
+    out = mgr.dict()
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_tail_worker, args=(2, os.path.join(d, "init"), M, problem, out), nprocs=2, join=True)
+    r0, r1 = out[0], out[1]
+    its = (0, 2) if problem == 'drone' else (1, 2)
+    R, nu, nfin = (60, 60, 6) if problem == 'drone' else (20, 40, 4)
+    n_rows, n_cols, indptr, indices = r0['pattern']
+    fr, fc, findptr, findices = r0['single_pattern']
+    assert r0['margin'] < 0 and r1['margin'] == r0['margin']
+    for it in its:
+        Ax, l, u, idx = r0[('tail', it)]
+        # every rank kept the K_r largest of its own shard; rank 0 holds their global indices
+        parts = []
+        for r in (r0, r1):
+            Zloc, sel, first = r[('local', it)]
+            assert np.array_equal(sel, _select_ref(Zloc, len(sel)))
+            parts.append(sel + first)
+        assert np.array_equal(idx, np.concatenate(parts))
+        fAx, fl, fu = r0[('single', it)]
+        A_full = sp.csc_matrix((fAx, findices, findptr), shape=(fr, fc))
+        As, ls, us_ = _submatrix(A_full, fl, fu, idx, M, R, nu, nfin)
+        assert (n_rows, n_cols) == As.shape and np.array_equal(indptr, As.indptr) and np.array_equal(indices, As.indices)
+        fin = indices < nfin
+        assert np.array_equal(Ax[~fin], As.data[~fin])            # bitwise: same kernel, same samples
+        assert np.allclose(Ax[fin], As.data[fin], rtol=1e-12, atol=1e-14)
+        assert np.array_equal(l[nfin:], ls[nfin:]) and np.array_equal(u[nfin:], us_[nfin:])
+        assert np.allclose(l[:nfin], ls[:nfin], rtol=1e-12, atol=1e-14) and np.allclose(u[:nfin], us_[:nfin], rtol=1e-12, atol=1e-14)
