@@ -472,11 +472,41 @@ def measure_target_config(args, rank, world, local_rank, device):
             asm.shared.close()
         del asm, path
         torch.cuda.empty_cache()
+    # tail-reduced subproblem (stratified selection per rank) delivered to rank 0 over NVLink
+    try:
+        DWs, masses, obs_Qs = synthetic_drone_samples(cnt, seed=100 + rank, device=device)
+        path = DevicePath(_lib.SAA_DRONE, 'saa', S, 0.1, cnt, M_global=M_total, sample_offset=first,
+                          device=local_rank)
+        path.set_params_drone(dp, dp.OSQP_TOL)
+        path.set_samples_drone(masses, DWs, obs_Qs)
+        torch.cuda.synchronize()
+        del DWs, masses, obs_Qs
+        path._keep = []
+        asm = sd.ShardedTailAssembler(path, margin=0.25)
+        for _ in range(3):
+            asm.step(us, 2)
+        torch.cuda.synchronize(); dist.barrier()
+        n = max(5, min(args.steps, 20))
+        t0 = time.perf_counter()
+        for _ in range(n):
+            asm.step(us, 2)
+        torch.cuda.synchronize(); dist.barrier()
+        t = torch.tensor([(time.perf_counter() - t0) / n], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        res["tail_ms"] = float(t.item()) * 1e3
+        res["tail_K_total"] = asm.K_total
+        asm.close()
+        del asm, path
+        torch.cuda.empty_cache()
+    except Exception as exc:
+        res["tail_error"] = repr(exc)[:200]
     res["note"] = ("host-timed between barriers, max over ranks; 'sharded' leaves row blocks in their owners' HBM, "
                    "'peer' = kernels store into rank 0's arrays over NVLink (fused gather), "
                    "'factored' = kernels store the factored record (sensitivities + trajectory, 3.4 instead of 9.1 KB "
                    "per sample) into rank 0 over NVLink and rank 0 expands it to the CSC entries, "
-                   "'nccl' = gather + merge kernel on rank 0")
+                   "'nccl' = gather + merge kernel on rank 0, "
+                   "'tail' = tail-reduced subproblem: every rank keeps the 1.25 alpha M_r samples of its shard with the "
+                   "largest constraint values and stores their rows into rank 0's K-sample matrix over NVLink")
     return res
 
 
