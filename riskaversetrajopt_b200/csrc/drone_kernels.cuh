@@ -34,9 +34,11 @@
 
 // ---- tuning switches (defaults = the measured best; history in profiles/README.md) ----
 #ifndef SAA_COPY
-#define SAA_COPY 4         // 4: 16-byte shared loads -> 16-byte streaming stores; 3: TMA bulk stores
-                           // (cp.async.bulk, correct but measured 2-3x slower on these short,
-                           // 16-byte-aligned runs)
+#define SAA_COPY 4         // 4: 16-byte shared loads -> 16-byte streaming stores (1.93 ms at M = 1e6);
+                           // 3: TMA bulk stores (cp.async.bulk with an L2 evict-first hint), double
+                           // buffered: correct, 2.6 ms (half the warps fit); single buffered with all 12
+                           // warps it ties at 1.97 ms -- the store pattern, not the copy mechanism, is
+                           // what bounds the kernel (profiles/README.md)
 #endif
 #ifndef SAA_BPS
 #define SAA_BPS 2          // resident blocks per SM the kernel is compiled for
