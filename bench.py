@@ -482,7 +482,7 @@ def measure_target_config(args, rank, world, local_rank, device):
         torch.cuda.synchronize()
         del DWs, masses, obs_Qs
         path._keep = []
-        asm = sd.ShardedTailAssembler(path, margin=0.25)
+        asm = sd.ShardedTailAssembler(path, margin=0.25, mode='factored')
         for _ in range(3):
             asm.step(us, 2)
         torch.cuda.synchronize(); dist.barrier()
@@ -506,7 +506,7 @@ def measure_target_config(args, rank, world, local_rank, device):
                    "per sample) into rank 0 over NVLink and rank 0 expands it to the CSC entries, "
                    "'nccl' = gather + merge kernel on rank 0, "
                    "'tail' = tail-reduced subproblem: every rank keeps the 1.25 alpha M_r samples of its shard with the "
-                   "largest constraint values and stores their rows into rank 0's K-sample matrix over NVLink")
+                   "largest constraint values and stores their factored record into rank 0 over NVLink, rank 0 expands it into its K-sample matrix")
     return res
 
 

@@ -247,9 +247,17 @@ class ShardedTailAssembler:
     ``offset_r .. offset_r + K_r`` of a matrix for ``K_total = sum K_r`` samples; the CVaR row keeps
     ``M_global alpha t`` and the expectation rows the mean over all ``M_global`` samples."""
 
-    def __init__(self, path, margin=0.25, K_local=None, group=None):
+    def __init__(self, path, margin=0.25, K_local=None, mode='peer', group=None):
+        """``mode='peer'``: the ranks' kernels store the CSC entries of their selected samples into
+        rank 0's arrays; ``mode='factored'`` (drone): they store the factored record (3.4 instead of
+        9.1 KB per sample cross NVLink) and rank 0 expands it, bitwise identically."""
         from .tail import TailSubproblem
-        self.path, self.group = path, group
+        from . import _lib
+        if mode not in ('peer', 'factored'):
+            raise ValueError("mode must be 'peer' or 'factored'")
+        if mode == 'factored' and path.problem != _lib.SAA_DRONE:
+            raise ValueError("the factored record exists for the drone only")
+        self.path, self.group, self.mode = path, group, mode
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         K = int(min(path.M_local, max(1, int(np.ceil((1.0 + margin) * path.alpha * path.M_local))))
                 if K_local is None else K_local)
@@ -261,9 +269,12 @@ class ShardedTailAssembler:
         sub = self.tail.sub
         n_rows, _, nnz = sub.pattern_sizes(False)
         npdt = np.float64 if sub.bits == 64 else np.float32
-        self.shared = SharedBuffers([nnz, n_rows, n_rows], npdt, sub.device, 0, group)
+        sizes = [nnz, n_rows, n_rows] + (list(sub.factored_sizes()) if mode == 'factored' else [])
+        self.shared = SharedBuffers(sizes, npdt, sub.device, 0, group)
         bufs = self.shared.tensors if self.rank == 0 else self.shared.ptrs
         self.out = dict(Ax=bufs[0], l=bufs[1], u=bufs[2], const_state=None)
+        if mode == 'factored':
+            self.fsp, self.fp = bufs[3], bufs[4]
         kmax = max(self.counts)                                  # all_gather wants equal sizes: pad
         self._idx_send = torch.zeros(kmax, dtype=torch.int64, device=sub.device)
         self._idx_all = [torch.empty(kmax, dtype=torch.int64, device=sub.device) for _ in self.counts]
@@ -280,7 +291,13 @@ class ShardedTailAssembler:
             raise ValueError("the sharded tail gather covers scp_iter >= 1 for the car")
         nccl = dist.get_backend(self.group) == 'nccl'
         us = broadcast_controls(us_mat, 0, self.group, device=p.device if nccl else None)
-        b = t.assemble(us, scp_iter, out=self.out, write_shared=(self.rank == 0), finalize=False)
+        if self.mode == 'factored' and self.rank != 0:
+            us = t.select(us)
+            t.sub.write_constants(self.out, scp_iter, write_shared=False)
+            t.sub.linearize_factored(us, scp_iter, self.fsp, self.fp, self.out['u'])
+            b = self.out
+        else:
+            b = t.assemble(us, scp_iter, out=self.out, write_shared=(self.rank == 0), finalize=False)
         all_reduce_sums(p.mean_sums, self.group)                 # sums over ALL samples of all ranks
         self._idx_send[:t.K] = t.idx + p.sample_offset
         dist.all_gather(self._idx_all, self._idx_send, group=self.group)
@@ -288,6 +305,9 @@ class ShardedTailAssembler:
         dist.barrier(group=self.group)                           # remote rows have landed in rank 0's HBM
         if self.rank != 0:
             return None, None
+        if self.mode == 'factored' and self.K_total > self.counts[0]:
+            t.sub.expand_factored(scp_iter, self.fsp, self.fp, self.counts[0], self.K_total - self.counts[0],
+                                  b['Ax'])
         t.finalize_means(b, scp_iter)
         return b, torch.cat([v[:c] for v, c in zip(self._idx_all, self.counts)])
 

@@ -116,7 +116,7 @@ def test_two_ranks_reproduce_single_gpu(problem, M):
             assert np.allclose(su[:nfin], u[:nfin], rtol=1e-12, atol=1e-14)      # global means on every rank
 
 
-def _tail_worker(rank, world, initfile, M, problem, out):
+def _tail_worker(rank, world, initfile, M, problem, mode, out):
     import torch
     import torch.distributed as dist
     from riskaversetrajopt_b200 import _lib, dist as sd
@@ -151,7 +151,7 @@ def _tail_worker(rank, world, initfile, M, problem, out):
             return p
     res = {}
     first, cnt = sd.shard_range(M, world, rank)
-    asm = sd.ShardedTailAssembler(make(first, cnt), margin=0.5)
+    asm = sd.ShardedTailAssembler(make(first, cnt), margin=0.5, mode=mode)
     for it in its:
         b, idx = asm.step(us if rank == 0 else np.zeros_like(us), it)
         Zloc = asm.tail.Z.cpu().numpy()
@@ -172,8 +172,9 @@ def _tail_worker(rank, world, initfile, M, problem, out):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("problem,M", [("drone", 1000), ("car", 600), ("drone", 77)])
-def test_two_ranks_tail_subproblem(problem, M):
+@pytest.mark.parametrize("problem,M,mode", [("drone", 1000, "peer"), ("car", 600, "peer"), ("drone", 77, "peer"),
+                                             ("drone", 1000, "factored"), ("drone", 77, "factored")])
+def test_two_ranks_tail_subproblem(problem, M, mode):
     """Stratified tail selection on 2 ranks, rows stored into rank 0's K-sample matrix over NVLink:
     the result is the single-GPU full matrix restricted to the selected samples."""
     import scipy.sparse as sp
@@ -185,7 +186,7 @@ def test_two_ranks_tail_subproblem(problem, M):
     mgr = mp.Manager()
     out = mgr.dict()
     with tempfile.TemporaryDirectory() as d:
-        mp.spawn(_tail_worker, args=(2, os.path.join(d, "init"), M, problem, out), nprocs=2, join=True)
+        mp.spawn(_tail_worker, args=(2, os.path.join(d, "init"), M, problem, mode, out), nprocs=2, join=True)
     r0, r1 = out[0], out[1]
     its = (0, 2) if problem == 'drone' else (1, 2)
     R, nu, nfin = (60, 60, 6) if problem == 'drone' else (20, 40, 4)
