@@ -333,6 +333,7 @@ __device__ __forceinline__ void car_pass(const CarArgs<T, S> &A, const CarEgo<T,
   const T dt = A.dt, wsdt = w_s * dt;
   T *cstage = stage + c * Ps::PER_C;
   T *ubrow = stage + Ps::UB + si * (S | 1);
+#pragma nv_diag_suppress 549                  // every chain is initialised at its birth step (k = j + 1) before use
   CarChain<T> ch[NJ > 0 ? NJ : 1];
   CarChain<T> cu{T(0), T(0), T(0), T(0)};     // tangent along u itself (for grad g . u)
   T zmax = -INFINITY;
@@ -342,7 +343,7 @@ __device__ __forceinline__ void car_pass(const CarArgs<T, S> &A, const CarEgo<T,
     const T dx = E.p[k][0] - qx, dy = E.p[k][1] - qy;
     const T n2 = fma(dx, dx, dy * dy);
     const T inv_n = rsqrt_t(n2);
-    const T nrm = n2 * inv_n;
+    [[maybe_unused]] const T nrm = n2 * inv_n;               // |d|: enters g_k in the first pass only
     const T nhx = dx * inv_n, nhy = dy * inv_n;
     // chains of this pass that are alive at state k: J0 <= j <= min(k-2, J1-1)
     constexpr int JE = (k - 1 < J1) ? (k - 1) : J1;          // exclusive end
