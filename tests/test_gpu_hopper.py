@@ -117,3 +117,25 @@ def test_friction_field_argument_ranges(pscale, atol):
     # determinism: the Hessian sums are reduced in a fixed order
     _, _, hs2 = m._friction(px, lam.reshape(-1))
     assert np.array_equal(hs, hs2)
+
+
+@pytest.mark.parametrize("pscale", [1.0, 5.0e3, 1.0e6])
+def test_friction_field_fp32_argument_ranges(pscale):
+    """FP32 handle: the branch-free float sincos covers |x| < 1e4, beyond that the chunk takes sincosf.
+    The reference values use the FP32-rounded inputs, so what is left is the FP32 arithmetic itself:
+    argument rounding ulp_32(|x|) per feature plus ~1e-7 relative per term."""
+    from oracle.oracle_hopper import HopperOracleB
+    from riskaversetrajopt_b200.hopper import hopper as hp
+    M = 1031
+    rs = np.random.RandomState(12)
+    f = tuple(a.astype(np.float32).astype(np.float64) for a in (
+        0.025 * np.sqrt(2 / 30) * rs.uniform(0, 1, (M, 30)), rs.uniform(0, np.pi, (M, 30)), rs.uniform(0, 2 * np.pi, (M, 30))))
+    m = hp.Model(M, 'saa', 0.1, f, precision='fp32')
+    b = HopperOracleB(M, 'saa', 0.1, *f)
+    px = (pscale * rs.uniform(-1, 1, 20)).astype(np.float32).astype(np.float64)
+    mu, dmu, _ = m._friction(px)
+    mu_b, dmu_b, _ = b.friction(px)
+    xmax = np.pi * np.abs(px).max() + 2 * np.pi
+    atol = 30 * 0.0065 * (np.spacing(np.float32(xmax)) + 4e-7)
+    assert np.allclose(mu, mu_b, rtol=1e-5, atol=atol)
+    assert np.allclose(dmu, dmu_b, rtol=1e-5, atol=atol * np.pi)
