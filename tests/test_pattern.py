@@ -52,3 +52,16 @@ def test_bad_arguments_are_reported(built_lib):
     from riskaversetrajopt_b200.pattern import pattern_sizes
     with pytest.raises(SaaError):
         pattern_sizes('drone', 'saa', 1, 5)
+
+
+def test_public_header_is_plain_c():
+    """include/saa_b200.h is the drop-in boundary: it must compile as C99 (no C++ or torch types)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        import pytest
+        pytest.skip("gcc not available")
+    hdr = os.path.join(os.path.dirname(__file__), "..", "include", "saa_b200.h")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", hdr],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
