@@ -56,6 +56,7 @@ def test_bad_arguments_are_reported(built_lib):
 
 def test_public_header_is_plain_c():
     """include/saa_b200.h is the drop-in boundary: it must compile as C99 (no C++ or torch types)."""
+    import os
     import shutil
     import subprocess
     if shutil.which("gcc") is None:
