@@ -1,5 +1,8 @@
-import sys, time, numpy as np, torch
-sys.path.insert(0, "/root/repo")
+"""Where the end-to-end step of bench.py spends its time: kernel, the three device-to-host copies
+(CUDA events), and the copy bandwidth for differently filled / allocated buffers.
+python tools/e2e_diag.py"""
+import os, sys, time, numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 from riskaversetrajopt_b200 import _lib
 from riskaversetrajopt_b200.device_path import DevicePath
