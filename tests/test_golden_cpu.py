@@ -1,7 +1,9 @@
-"""Oracle-B against the committed golden vectors (minted from Oracle-A)."""
+"""Oracle-B against the committed golden vectors: those minted from Oracle-A (make_golden.py) and
+those minted by executing the reference's own source (ref_*, make_golden_ref.py)."""
 import os
 
 import numpy as np
+import pytest
 
 from oracle.oracle_b import DroneOracleB
 from riskaversetrajopt_b200.drone import drone_params as dp
@@ -10,8 +12,9 @@ from conftest import rel_err
 G = os.path.join(os.path.dirname(__file__), "golden")
 
 
-def test_drone_m50_golden(drone_seed0):
-    g = np.load(os.path.join(G, "drone_M50_saa_iter2.npz"))
+@pytest.mark.parametrize("src", ["", "ref_"], ids=["oracle_a", "reference_exec"])
+def test_drone_m50_golden(drone_seed0, src):
+    g = np.load(os.path.join(G, src + "drone_M50_saa_iter2.npz"))
     DWs, masses, obs_Qs = drone_seed0
     b = DroneOracleB(dp.S, DWs, masses, obs_Qs, 'saa', 0.1)
     A, l, u = b.get_constraints_coeffs(g["us"], 2)
@@ -24,8 +27,9 @@ def test_drone_m50_golden(drone_seed0):
     assert np.allclose(b.monte_carlo_constraints(g["us"])[1], g["Z"], rtol=1e-12, atol=1e-13)
 
 
-def test_drone_m8_branches_golden(drone_seed0):
-    g = np.load(os.path.join(G, "drone_M8_branches.npz"))
+@pytest.mark.parametrize("src", ["", "ref_"], ids=["oracle_a", "reference_exec"])
+def test_drone_m8_branches_golden(drone_seed0, src):
+    g = np.load(os.path.join(G, src + "drone_M8_branches.npz"))
     DWs, masses, obs_Qs = (x[:8] for x in drone_seed0)
     for method in ('saa', 'baseline'):
         for variant in ('risk', 'times'):

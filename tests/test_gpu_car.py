@@ -50,9 +50,10 @@ def test_model_constructor_draws_like_the_reference():
         (m.states_init, m.omegas_speed, m.omegas_repulsive, m.DWs), s))
 
 
-def test_golden():
+@pytest.mark.parametrize("src", ["", "ref_"], ids=["oracle_a", "reference_exec"])
+def test_golden(src):
     from riskaversetrajopt_b200.car.driving import Model
-    g = np.load(os.path.join(G, "car_M50_saa.npz"))
+    g = np.load(os.path.join(G, src + "car_M50_saa.npz"))
     model = Model(50, 'saa', 0.05, samples=_seed0())
     assert np.array_equal(model.initial_guess_us_mat(), g["us0"])
     for name, us, it in (("iter0", g["us0"], 0), ("iter1", g["us1"], 1), ("iter2", g["us1"], 2)):

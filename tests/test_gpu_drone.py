@@ -57,8 +57,9 @@ def test_reference_config_matches_oracle(drone_seed0, method, variant, scp_iter)
     _check(*model.get_constraints_coeffs(us, scp_iter), *ref.get_constraints_coeffs(us, scp_iter), RTOL64)
 
 
-def test_golden_m50(drone_seed0):
-    g = np.load(os.path.join(G, "drone_M50_saa_iter2.npz"))
+@pytest.mark.parametrize("src", ["", "ref_"], ids=["oracle_a", "reference_exec"])
+def test_golden_m50(drone_seed0, src):
+    g = np.load(os.path.join(G, src + "drone_M50_saa_iter2.npz"))
     model, _ = _models(drone_seed0, 50)
     assert np.array_equal(model.initial_guess_us_mat(), g["us"])
     A, l, u = model.get_constraints_coeffs(g["us"], 2)
@@ -75,8 +76,9 @@ def test_golden_m50(drone_seed0):
     assert np.array_equal(sat, g["Z"] <= 1e-6)
 
 
-def test_golden_m8_branches(drone_seed0):
-    g = np.load(os.path.join(G, "drone_M8_branches.npz"))
+@pytest.mark.parametrize("src", ["", "ref_"], ids=["oracle_a", "reference_exec"])
+def test_golden_m8_branches(drone_seed0, src):
+    g = np.load(os.path.join(G, src + "drone_M8_branches.npz"))
     for method in ('saa', 'baseline'):
         for variant in ('risk', 'times'):
             model, _ = _models(drone_seed0, 8, method, 0.05, variant)

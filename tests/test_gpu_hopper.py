@@ -21,10 +21,11 @@ def _dense(shape, r, c, v):
     return D
 
 
+@pytest.mark.parametrize("src", ["", "ref_"], ids=["oracle_a", "reference_exec"])
 @pytest.mark.parametrize("method", ["saa", "baseline"])
-def test_golden_values_jacobian_hessian(method):
+def test_golden_values_jacobian_hessian(method, src):
     from riskaversetrajopt_b200.hopper import hopper as hp
-    g = np.load(os.path.join(G, "hopper_M30.npz"))
+    g = np.load(os.path.join(G, src + "hopper_M30.npz"))
     Z = g["Z"]
     m = hp.Model(hp.M, method, 0.2, _feats())
     nv = hp.num_vars(hp.M)

@@ -44,8 +44,9 @@ def test_a_equals_b(car_seed0, method):
         assert np.allclose(l[f], lb[f], rtol=1e-12, atol=1e-13) and np.allclose(u, ub, rtol=1e-11, atol=1e-12)
 
 
-def test_golden(car_seed0):
-    g = np.load(os.path.join(G, "car_M50_saa.npz"))
+@pytest.mark.parametrize("src", ["", "ref_"], ids=["oracle_a", "reference_exec"])
+def test_golden(car_seed0, src):
+    g = np.load(os.path.join(G, src + "car_M50_saa.npz"))
     b = CarOracleB(*car_seed0, 'saa', 0.05)
     for name, us, it in (("iter0", g["us0"], 0), ("iter1", g["us1"], 1), ("iter2", g["us1"], 2)):
         A, l, u = b.get_constraints_coeffs(us, it)
