@@ -17,8 +17,12 @@
  *   - a handle is not re-entrant: one host thread per handle; one process per
  *     GPU for multi-GPU runs.  All device work is stream-ordered on `stream`
  *     and asynchronous unless stated otherwise.
- *   - precision: 64 -> all device buffers are double; 32 -> float (inputs to
- *     saa_set_samples_* are always double in the reference layouts).
+ *   - precision: 64 -> every output buffer (Ax, l, u, Z, Xs, factored record, hopper g / jac)
+ *     is double; 32 -> float: the STORAGE precision of the outputs (half the HBM / NVLink / PCIe
+ *     bytes).  The arithmetic is FP64 in both modes (the packed samples stay double), so FP32
+ *     results are the FP64 results rounded once: per-entry relative error <= 6e-8, inside the
+ *     1e-4 the FP32 mode promises even for entries that are small by cancellation.  Inputs to
+ *     saa_set_samples_*, us_host, mean sums and CVaR / Hessian sums are always double.
  *
  * QP variable order (reference drone/drone_risk.py:226,381): z = (u[0..n_u*S),
  * y[0..M), slack, t).  Constraint-row order (drone_risk.py:282-374, :401-423):
@@ -42,7 +46,8 @@ typedef enum {
   SAA_ERR_ARG = -1,        /* bad argument / unsupported configuration        */
   SAA_ERR_CUDA = -2,       /* a CUDA runtime call failed                      */
   SAA_ERR_STATE = -3,      /* call order violated (e.g. samples not set)      */
-  SAA_ERR_NO_DEVICE = -4   /* no usable CUDA device (there is NO CPU fallback)*/
+  SAA_ERR_NO_DEVICE = -4,  /* no usable CUDA device (there is NO CPU fallback)*/
+  SAA_ERR_NONFINITE = -5   /* saa_check_finite: a rollout produced NaN / Inf  */
 } saa_status;
 
 typedef enum { SAA_DRONE = 0, SAA_CAR = 1, SAA_HOPPER = 2 } saa_problem;
@@ -230,6 +235,14 @@ int saa_rollout(saa_handle *h, const double *us_host, void *Xs_dev, void *stream
 int saa_cvar_terms(saa_handle *h, const double *us_host, double t_risk,
                    double sat_tol, void *Z_dev, double *out3_dev, void *stream);
 
+/*
+ * Non-finite guard.  The car divides by |p_ego - p_ped| (car/driving.py:154); the reference
+ * silently propagates NaN when the two coincide.  Every assemble / rollout launch counts the
+ * samples whose rollout met a zero or non-finite distance (one atomicAdd per warp, on the
+ * device).  saa_check_finite synchronises `stream`, reads and clears the counter, stores it in
+ * *count_out (may be NULL) and returns SAA_ERR_NONFINITE if it is non-zero.                  */
+int saa_check_finite(saa_handle *h, int64_t *count_out, void *stream);
+
 /* ---- hopper slip-risk (hopper/hopper.py:300-367 and its derivatives) ------ */
 /* replaces: intensities/thetas/taus (hopper/hopper.py:68-74), each (M, n_feat)*/
 int saa_set_samples_hopper(saa_handle *h, int32_t n_features, double mu_nom,
@@ -248,6 +261,44 @@ int saa_hopper_friction(saa_handle *h, int32_t n_c, const double *px_host,
                         void *mu_dev, void *dmu_dev, const double *lambda_dev,
                         double *hess_sums_dev, void *stream);
 
+/*
+ * Device-side assembly of the slip-risk block of the hopper NLP.  The evaluation point is
+ * given by the O(n_c) contact geometry the host extracts from the decision vector
+ * (hopper/hopper.py:106-112, :166-171, :305-311) plus the M risk variables y (device):
+ */
+typedef struct {
+  int32_t n_c;                /* contact instants (<= 32); reference: 20           */
+  double px[32];              /* end-effector x = x0 + x3 sin x2 at the contact    */
+  double fx[32], fz[32];      /* contact forces us[t, 2], us[t, 3]                 */
+  double x2[32], x3[32];      /* leg angle and length (for d px / d(x0, x2, x3))   */
+  double t_risk, slack;       /* Z[-1], Z[-2]                                      */
+} saa_hopper_point;
+/* g_dev[n_rows]: saa      [M alpha t + sum y] [-y_i (M)] [f_x - mu_i(p) f_z - t - y_i - slack (i-major,
+ *                          contact-minor)] [0]          n_rows = 1 + M + M n_c + 1
+ *                baseline [f_x - mu_i(p) f_z - slack]   n_rows = M n_c          (y_dev may be NULL)
+ * replaces: slip_risk_constraints as consumed by eval_g (hopper/hopper.py:300-367, :591-593). */
+int saa_hopper_g(saa_handle *h, const saa_hopper_point *pt, const double *y_dev, void *g_dev,
+                 void *stream);
+/* jac_dev[4 * M n_c]: the entries of the slip-risk rows that depend on the iterate, as four
+ * arrays of M n_c values (index i n_c + c): d row / d x0, d x2, d x3 (= -f_z mu_i'(p) (1, x3 cos x2,
+ * sin x2)) and d row / d f_z (= -mu_i(p)).  The other entries are the constants 1 (f_x), -1
+ * (y_i, slack, t), 1 and M alpha (row 0), -1 (rows -y_i).
+ * replaces: the slip-risk slice of jacrev(g) in eval_jac_g (hopper/hopper.py:569, :594-596). */
+int saa_hopper_jac(saa_handle *h, const saa_hopper_point *pt, void *jac_dev, void *stream);
+/* hess_dev[10 * n_c] (always double): per contact the lower triangle of the symmetric block of
+ * hessian(lambda . g) on (x0, x2, x3, f_z)_t, as ten arrays of n_c values in the order (0,0) (1,0)
+ * (1,1) (2,0) (2,1) (2,2) (3,0) (3,1) (3,2) (3,3); lambda_dev: the M n_c multipliers of the sample
+ * rows.  Local samples only: all-reduce(sum) across ranks.
+ * replaces: the slip-risk part of hess_lagrange_dot_g in eval_h (hopper/hopper.py:575-580, :622-628). */
+int saa_hopper_hess(saa_handle *h, const saa_hopper_point *pt, const double *lambda_dev,
+                    double *hess_dev, void *stream);
+/* Monte-Carlo terms: Z_i = max_c (f_x - mu_i(p) f_z) into Z_dev (may be NULL) and out3_dev =
+ * [sum_i max(Z_i - t_risk, 0), #{Z_i <= sat_tol}, max_i Z_i] with t_risk = pt->t_risk.
+ * replaces: no_slip_constraints_verification and the closed form of avar
+ * (hopper/hopper.py:910-925, :957).                                                           */
+int saa_hopper_cvar_terms(saa_handle *h, const saa_hopper_point *pt, double sat_tol, void *Z_dev,
+                          double *out3_dev, void *stream);
+
 /* ---- tail-reduced subproblem (no reference counterpart) ----
  * At the solution of the Rockafellar-Uryasev program (drone/drone_risk.py:327-368,
  * car/driving.py:331-372) only the samples in the upper alpha-tail of
@@ -265,7 +316,7 @@ int saa_hopper_friction(saa_handle *h, int32_t n_c, const double *px_host,
 int saa_linearize_means(saa_handle *h, const double *us_host, void *Z_dev,
                         double *mean_sums_dev, void *stream);
 /* idx_out_dev[0..K): indices (ascending) of the K largest of the M_local values
- * Z_dev (handle precision); ties at the threshold go to the smaller index.
+ * Z_dev (storage precision of the handle); ties at the threshold go to the smaller index.
  * Exact and deterministic (radix select + ordered compaction).                  */
 int saa_select_tail(saa_handle *h, const void *Z_dev, int64_t K,
                     int64_t *idx_out_dev, void *stream);

@@ -26,6 +26,12 @@ class DroneParams(C.Structure):
                 ("osqp_tol", C.c_double)]
 
 
+class HopperPoint(C.Structure):
+    _fields_ = [("n_c", C.c_int32), ("px", C.c_double * 32), ("fx", C.c_double * 32),
+                ("fz", C.c_double * 32), ("x2", C.c_double * 32), ("x3", C.c_double * 32),
+                ("t_risk", C.c_double), ("slack", C.c_double)]
+
+
 class CarParams(C.Structure):
     _fields_ = [("dt", C.c_double), ("u_max", C.c_double), ("beta", C.c_double),
                 ("speed_ped_des", C.c_double), ("min_separation_distance", C.c_double),
@@ -81,6 +87,11 @@ _PROTOTYPES = {
                                          C.c_void_p, C.c_void_p]),
     "saa_hopper_friction": (C.c_int, [_H, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p]),
+    "saa_check_finite": (C.c_int, [_H, C.POINTER(C.c_int64), C.c_void_p]),
+    "saa_hopper_g": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "saa_hopper_jac": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "saa_hopper_hess": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "saa_hopper_cvar_terms": (C.c_int, [_H, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
     "saa_linearize_means": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "saa_select_tail": (C.c_int, [_H, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "saa_gather_samples": (C.c_int, [_H, _H, C.c_void_p, C.c_void_p]),

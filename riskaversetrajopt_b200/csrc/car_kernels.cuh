@@ -183,7 +183,7 @@ template <int S, int J> struct CarCol {
   static constexpr i64 CB0 = 2 * J * (S - 1) - J * (J - 1), CB1 = CB0 + L;
 };
 
-template <typename T, int S> struct CarArgs {
+template <typename T, typename TO, int S> struct CarArgs {
   const T *x0;       // packed [f*Mpad + s], f = 0..3: pedestrian (qx, qy, wx, wy) initial
   const T *om;       // packed [f*Mpad + s], f = 0: omega_speed, 1: omega_repulsive
   const T *dw;       // packed [(k*2+f)*Mpad + s], f = 0,1: noise on states 6,7
@@ -193,10 +193,11 @@ template <typename T, int S> struct CarArgs {
   T goal[4];
   T dt, noise_c, v_des, d_min;
   T ztol;
-  T *Ax; i64 M_out, first_out;
-  T *ub; i64 ub_off;
-  T *Z;
+  TO *Ax; i64 M_out, first_out;   // TO = storage type of the outputs (double | float), T = arithmetic type
+  TO *ub; i64 ub_off;
+  TO *Z;
   double *sums;      // CarRed<S>::N doubles: M * (sample-independent final-row values)
+  unsigned long long *nonfinite;   // += number of samples whose rollout met |d| = 0 / a non-finite value
 };
 
 // Ego trajectory, shared by the whole block
@@ -233,8 +234,8 @@ __device__ void car_ego_rollout(const T *us, const T *ego0, T dt, CarEgo<T, S> &
 
 // sample-independent final rows (car/driving.py:217-221, :271, :311-313):
 // sums[r] = M * value so that the generic "sum / M_global" finalize applies across ranks
-template <typename T, int S>
-__device__ void car_final_rows(const CarArgs<T, S> &A, const CarEgo<T, S> &E, int tid, int nthreads) {
+template <typename T, typename TO, int S>
+__device__ void car_final_rows(const CarArgs<T, TO, S> &A, const CarEgo<T, S> &E, int tid, int nthreads) {
   using Rd = CarRed<S>;
   const double Md = (double)A.M;
   for (int r = tid; r < Rd::N; r += nthreads) {
@@ -259,82 +260,129 @@ __device__ void car_final_rows(const CarArgs<T, S> &A, const CarEgo<T, S> &E, in
   }
 }
 
-
-
 // per-chain sensitivity state
 template <typename T> struct CarChain { T rx, ry, wx, wy; };
 
 #ifndef SAA_CAR_WARPS
-#define SAA_CAR_WARPS 12   // warps per block (one block per SM; shared memory = WARPS x CarPass::SIZE)
+#define SAA_CAR_WARPS 12   // warps per block (one block per SM; shared memory = WARPS x (geometry + staging))
 #endif
-#ifndef SAA_CAR_NPASS
-#define SAA_CAR_NPASS 4    // the S-1 chains of a control are processed in NPASS groups, see CarPass
+#ifndef SAA_CAR_CAP
+#define SAA_CAR_CAP 38     // staged values per sample and control in one chain pass (>= S-1); see CarPass
 #endif
 
-// The chains (control steps j) of a tile are processed in NPASS passes over the horizon so that
-// only part of the tile's entries is staged at a time: with 4 passes staging drops from 51 KB to 16 KB per
-// warp, i.e. 12 instead of 4 resident warps per SM (1.72 -> 1.36 ms at M = 1e6); the price is that the (cheap) rollout and
-// geometry are recomputed in every pass.  Group boundaries balance the staged sizes.
-template <int S, int NPASS> struct CarPass {
+// Kernel structure (round 2).  A warp owns a tile of 16 samples, lane = (sample, control c).
+//   pass A   rollout of the pedestrian ONCE per tile: per state k the unit vector n_k = d_k/|d_k|
+//            and om_k = dt w_r / |d_k| go to shared memory (3 doubles per sample and step); the
+//            tangent along u itself gives grad g . u for the upper bounds; Z_i.  The noise
+//            increments are parked in the (still idle) staging buffer, not in 80 registers.
+//   pass p   the forward-sensitivity chains j in [J0, J1) of this lane's control, all advancing
+//            together over k = J0+1..S from the stored geometry (no rollout, no rsqrt, G_k rebuilt
+//            with 5 flops); their entries are staged in CSC order [c][j][sample][k] and streamed
+//            out as 16-byte stores.  Consecutive chains are packed into a pass while their padded
+//            lengths fit SAA_CAR_CAP values per sample.
+// Round 1 recomputed rollout + rsqrt in every pass and kept the noise in registers over all of
+// them (168 registers, 160 B of spills, 12 warps/SM): 1.36 ms at M = 1e6.
+template <int S, int CAP> struct CarPass {
+  static_assert(CAP >= ((S - 1) | 1), "SAA_CAR_CAP must hold the longest chain");
   __host__ __device__ static constexpr int bound(int p) {           // first chain of pass p
-    if (NPASS == 1) return p == 0 ? 0 : S - 1;
-    const int total = (S - 1) * S / 2;
-    int acc = 0, j = 0, q = 0;
-    while (q < p && j < S - 1) {
-      acc += S - 1 - j; ++j;
-      if (acc * NPASS >= total * (q + 1)) ++q;
+    int j = 0;
+    for (int q = 0; q < p && j < S - 1; ++q) {
+      int acc = 0;
+      while (j < S - 1 && acc + ((S - 1 - j) | 1) <= CAP) { acc += (S - 1 - j) | 1; ++j; }
     }
-    return p >= NPASS ? S - 1 : j;
+    return j;
   }
+  __host__ __device__ static constexpr int npass() {
+    int p = 0;
+    while (bound(p) < S - 1) ++p;
+    return p;
+  }
+  static constexpr int NPASS = npass();
   __host__ __device__ static constexpr int pre(int j0, int j) {     // staging offset of column j inside its pass
     int s = 0;
     for (int jj = j0; jj < j; ++jj) s += kTileSamples * ((S - 1 - jj) | 1);
     return s;
   }
-  __host__ __device__ static constexpr int per_control() {          // largest staged block of one control
-    int m = 0;
-    for (int p = 0; p < NPASS; ++p) { const int v = pre(bound(p), bound(p + 1)); m = v > m ? v : m; }
-    return m;
+  static constexpr int PER_C = kTileSamples * CAP;                  // staged block of one control
+  static constexpr int UBROW = S | 1;
+  // pass A parks the noise [2][S][16] (in T) and stages the upper-bound rows 16 x UBROW (in TO)
+  __host__ __device__ static constexpr int stage_bytes(int szT, int szTO) {
+    const int a = 2 * S * kTileSamples * szT + kTileSamples * UBROW * szTO;
+    const int b = 2 * PER_C * szTO;
+    return ((a > b ? a : b) + 15) / 16 * 16;
   }
-  static constexpr int PER_C = per_control();
-  static constexpr int UB = 2 * PER_C;          // upper-bound rows: 16 x (S|1), first pass only
-  static constexpr int SIZE = UB + kTileSamples * (S | 1);
 };
 
-template <typename T, int S, int WARPS> struct CarSmem {
+template <typename T, typename TO, int S, int WARPS> struct CarSmem {
+  using Ps = CarPass<S, SAA_CAR_CAP>;
+  static constexpr int STAGE_BYTES = Ps::stage_bytes((int)sizeof(T), (int)sizeof(TO));
   CarEgo<T, S> ego;
-  T stage[WARPS][CarPass<S, SAA_CAR_NPASS>::SIZE];
+  T geo[WARPS][3][S + 1][kTileSamples];                  // n_x, n_y, om per sample and state
+  alignas(16) unsigned char stage[WARPS][STAGE_BYTES];
 };
 
-template <typename T, int S, int J0, int J, int J1>
-__device__ __forceinline__ void car_copy_cols(const CarArgs<T, S> &A, const T *stage, i64 sbase, int ns,
+// Copy a column run (ns samples x L values, rows of stride STRIDE in shared memory) to its
+// contiguous place in global memory with 16-byte streaming stores; the run starts 8-byte (4-byte)
+// aligned only, so up to VEC-1 head / tail elements go out as scalars.
+template <typename TO, int L, int STRIDE>
+__device__ __forceinline__ void car_copy_run(TO *__restrict__ dst, const TO *__restrict__ src, int n, int lane) {
+  constexpr int VEC = 16 / (int)sizeof(TO);
+  auto at = [&](int e) -> TO { const int row = e / L; return src[e + row * (STRIDE - L)]; };
+  const int head = min(n, (int)((VEC - (((uintptr_t)dst / sizeof(TO)) & (VEC - 1))) & (VEC - 1)));
+  const int nvec = (n - head) / VEC, tail = n - head - nvec * VEC;
+  if (lane < head) st_stream(dst + lane, at(lane));
+#pragma unroll 2
+  for (int v = lane; v < nvec; v += 32) {
+    const int e = head + v * VEC;
+    if constexpr (VEC == 2) {
+      double2 val;
+      val.x = (double)at(e); val.y = (double)at(e + 1);
+      __stcs(reinterpret_cast<double2 *>(dst + e), val);
+    } else {
+      float4 val;
+      val.x = (float)at(e); val.y = (float)at(e + 1); val.z = (float)at(e + 2); val.w = (float)at(e + 3);
+      __stcs(reinterpret_cast<float4 *>(dst + e), val);
+    }
+  }
+  if (lane < tail) st_stream(dst + head + nvec * VEC + lane, at(head + nvec * VEC + lane));
+}
+
+template <typename T, typename TO, int S, int J0, int J, int J1>
+__device__ __forceinline__ void car_copy_cols(const CarArgs<T, TO, S> &A, const TO *stage, i64 sbase, int ns,
                                               int lane) {
   if constexpr (J < J1) {
     using C = CarCol<S, J>;
-    using Ps = CarPass<S, SAA_CAR_NPASS>;
+    using Ps = CarPass<S, SAA_CAR_CAP>;
     i64 sb = sbase, mout = A.M_out;
     opaque(sb); opaque(mout);   // 2 IMADs per column instead of 2(S-1) live 64-bit bases
-    copy_run<T, C::L, C::STRIDE>(A.Ax + (C::CA0 + mout * C::CB0 + sb * C::L), stage + Ps::pre(J0, J),
-                                 ns * C::L, lane);
-    copy_run<T, C::L, C::STRIDE>(A.Ax + (C::CA1 + mout * C::CB1 + sb * C::L),
-                                 stage + Ps::PER_C + Ps::pre(J0, J), ns * C::L, lane);
-    car_copy_cols<T, S, J0, J + 1, J1>(A, stage, sbase, ns, lane);
+    car_copy_run<TO, C::L, C::STRIDE>(A.Ax + (C::CA0 + mout * C::CB0 + sb * C::L), stage + Ps::pre(J0, J),
+                                      ns * C::L, lane);
+    car_copy_run<TO, C::L, C::STRIDE>(A.Ax + (C::CA1 + mout * C::CB1 + sb * C::L),
+                                      stage + Ps::PER_C + Ps::pre(J0, J), ns * C::L, lane);
+    car_copy_cols<T, TO, S, J0, J + 1, J1>(A, stage, sbase, ns, lane);
   }
 }
 
-// One pass over the horizon for the chains j in [J0, J1) of this lane's control c.
-// FIRST: also the upper bounds, Z_i (values that do not depend on the chain group).
-template <typename T, int S, int J0, int J1, bool FIRST>
-__device__ __forceinline__ void car_pass(const CarArgs<T, S> &A, const CarEgo<T, S> &E, T *stage, int c,
-                                         int si, T qx, T qy, T wx, T wy, T w_s, T w_r,
-                                         const T (&dwx)[S], const T (&dwy)[S], T &zmax_out) {
-  using Ps = CarPass<S, SAA_CAR_NPASS>;
-  constexpr int NJ = J1 - J0;
-  const T dt = A.dt, wsdt = w_s * dt;
-  T *cstage = stage + c * Ps::PER_C;
-  T *ubrow = stage + Ps::UB + si * (S | 1);
-#pragma nv_diag_suppress 549                  // every chain is initialised at its birth step (k = j + 1) before use
-  CarChain<T> ch[NJ > 0 ? NJ : 1];
+// pass A: rollout, geometry -> shared memory, upper bounds, Z_i
+template <typename T, typename TO, int S>
+__device__ __forceinline__ void car_rollout_pass(const CarArgs<T, TO, S> &A, const CarEgo<T, S> &E,
+                                                 T (*geo)[S + 1][kTileSamples], unsigned char *stage_raw,
+                                                 int c, int si, i64 s, T w_s, T w_r, T &zmax_out, bool &bad) {
+  using Ps = CarPass<S, SAA_CAR_CAP>;
+  T (*dws)[S][kTileSamples] = reinterpret_cast<T (*)[S][kTileSamples]>(stage_raw);           // [2][S][16]
+  TO *ubrow = reinterpret_cast<TO *>(stage_raw + 2 * S * kTileSamples * sizeof(T)) + si * Ps::UBROW;
+  // this lane's half of the noise (c = 0: state 6, c = 1: state 7), all loads in flight at once
+  {
+    T tmp[S];
+#pragma unroll
+    for (int k = 0; k < S; ++k) tmp[k] = __ldcs(A.dw + (i64)(2 * k + c) * A.Mpad + s);
+#pragma unroll
+    for (int k = 0; k < S; ++k) dws[c][k][si] = tmp[k];
+  }
+  T qx = __ldcs(A.x0 + s), qy = __ldcs(A.x0 + A.Mpad + s);
+  T wx = __ldcs(A.x0 + 2 * A.Mpad + s), wy = __ldcs(A.x0 + 3 * A.Mpad + s);
+  __syncwarp();
+  const T dt = A.dt, wsdt = w_s * dt, dtwr = dt * w_r;
   CarChain<T> cu{T(0), T(0), T(0), T(0)};     // tangent along u itself (for grad g . u)
   T zmax = -INFINITY;
   static_for<0, S + 1>([&](auto kc) {
@@ -343,100 +391,126 @@ __device__ __forceinline__ void car_pass(const CarArgs<T, S> &A, const CarEgo<T,
     const T dx = E.p[k][0] - qx, dy = E.p[k][1] - qy;
     const T n2 = fma(dx, dx, dy * dy);
     const T inv_n = rsqrt_t(n2);
-    [[maybe_unused]] const T nrm = n2 * inv_n;               // |d|: enters g_k in the first pass only
+    bad |= !(n2 > T(0)) || !(n2 < T(INFINITY));
     const T nhx = dx * inv_n, nhy = dy * inv_n;
-    // chains of this pass that are alive at state k: J0 <= j <= min(k-2, J1-1)
-    constexpr int JE = (k - 1 < J1) ? (k - 1) : J1;          // exclusive end
+    const T om_n = dtwr * inv_n;
+    if (c == 0) { geo[0][k][si] = nhx; geo[2][k][si] = om_n; }
+    else geo[1][k][si] = nhy;
     if constexpr (k >= 1) {
-      // row k of the sample: d g_k / d u_{j,c} = -n_k . rho_k^{(j,c)}
-      static_for<J0, (JE > J0 ? JE : J0)>([&](auto jc) {
-        constexpr int j = decltype(jc)::value;
-        cstage[Ps::pre(J0, j) + si * CarCol<S, j>::STRIDE + (k - j - 2)] =
-            -fma(nhx, ch[j - J0].rx, nhy * ch[j - J0].ry);
-      });
-      if constexpr (FIRST) {
-        // upper bound -g_k + grad g_k . u (:278), grad g . u summed over both controls
-        T gu = -fma(nhx, cu.rx, nhy * cu.ry);
-        gu += __shfl_xor_sync(0xffffffffu, gu, 16);
-        const T g = A.d_min - nrm;
-        zmax = fmax(zmax, g);
-        if (c == (k & 1)) ubrow[k - 1] = gu - g;
-      }
+      // upper bound -g_k + grad g_k . u (:278), grad g . u summed over both controls
+      T gu = -fma(nhx, cu.rx, nhy * cu.ry);
+      gu += __shfl_xor_sync(0xffffffffu, gu, 16);
+      const T g = A.d_min - n2 * inv_n;
+      zmax = fmax(zmax, g);
+      if (c == (k & 1)) ubrow[k - 1] = (TO)(gu - g);
     }
     if constexpr (k < S) {
-      // one Euler-Maruyama step and its linearisation
-      const T om_n = dt * w_r * inv_n;
       const T g11 = -om_n * fma(-nhx, nhx, T(1)), g12 = om_n * nhx * nhy,
               g22 = -om_n * fma(-nhy, nhy, T(1));             // dt * dF/dp_ego
       const T ttx = E.tt[c][k][0], tty = E.tt[c][k][1];
-      static_for<J0, (JE > J0 ? JE : J0)>([&](auto jc) {
-        constexpr int j = decltype(jc)::value;
-        CarChain<T> &h = ch[j - J0];
-        const T sy = wsdt * h.wy;
-        const T nwx = fma(g11, h.rx, fma(g12, h.ry, h.wx - sy));
-        const T nwy = fma(g12, h.rx, fma(g22, h.ry, h.wy - sy));
-        h.rx = fma(-dt, h.wx, h.rx + ttx);
-        h.ry = fma(-dt, h.wy, h.ry + tty);
-        h.wx = nwx; h.wy = nwy;
-      });
-      // chain j = k-1 is born at this step: rho_{k+1} = T_c(k), w_{k+1} = 0
-      if constexpr (k >= 1 && k - 1 >= J0 && k - 1 < J1) {
-        ch[k - 1 - J0].rx = ttx; ch[k - 1 - J0].ry = tty; ch[k - 1 - J0].wx = T(0); ch[k - 1 - J0].wy = T(0);
-      }
-      if constexpr (FIRST) {
-        const T uc = E.ucum[c][k];
-        const T sy = wsdt * cu.wy;
-        const T nwx = fma(g11, cu.rx, fma(g12, cu.ry, cu.wx - sy));
-        const T nwy = fma(g12, cu.rx, fma(g22, cu.ry, cu.wy - sy));
-        cu.rx = fma(-dt, cu.wx, fma(uc, ttx, cu.rx));
-        cu.ry = fma(-dt, cu.wy, fma(uc, tty, cu.ry));
-        cu.wx = nwx; cu.wy = nwy;
-      }
+      const T uc = E.ucum[c][k];
+      const T sy = wsdt * cu.wy;
+      const T nwx = fma(g11, cu.rx, fma(g12, cu.ry, cu.wx - sy));
+      const T nwy = fma(g12, cu.rx, fma(g22, cu.ry, cu.wy - sy));
+      cu.rx = fma(-dt, cu.wx, fma(uc, ttx, cu.rx));
+      cu.ry = fma(-dt, cu.wy, fma(uc, tty, cu.ry));
+      cu.wx = nwx; cu.wy = nwy;
+      // one Euler-Maruyama step of the pedestrian (:187-204)
       const T sp = w_s * (A.v_des - wy);
       const T fx = fma(-w_r, nhx, sp), fy = fma(-w_r, nhy, sp);
       const T nqx = fma(dt, wx, qx), nqy = fma(dt, wy, qy);
-      wx = wx + dt * fx + A.noise_c * dwx[k];
-      wy = wy + dt * fy + A.noise_c * dwy[k];
+      wx = wx + dt * fx + A.noise_c * dws[0][k][si];
+      wy = wy + dt * fy + A.noise_c * dws[1][k][si];
       qx = nqx; qy = nqy;
     }
   });
   zmax_out = zmax;
 }
 
-template <typename T, int S, int P>
-__device__ __forceinline__ void car_passes(const CarArgs<T, S> &A, const CarEgo<T, S> &E, T *stage, int c,
-                                           int si, int lane, i64 s, i64 s0, int ns, bool active, T qx,
-                                           T qy, T wx, T wy, T w_s, T w_r, const T (&dwx)[S],
-                                           const T (&dwy)[S]) {
-  using Ps = CarPass<S, SAA_CAR_NPASS>;
-  if constexpr (P < SAA_CAR_NPASS) {
+// One pass over the horizon for the chains j in [J0, J1) of this lane's control c, driven by the
+// geometry pass A left in shared memory.
+template <typename T, typename TO, int S, int J0, int J1>
+__device__ __forceinline__ void car_chain_pass(const CarArgs<T, TO, S> &A, const CarEgo<T, S> &E,
+                                               const T (*geo)[S + 1][kTileSamples], TO *stage, int c, int si,
+                                               T wsdt) {
+  using Ps = CarPass<S, SAA_CAR_CAP>;
+  constexpr int NJ = J1 - J0;
+  const T dt = A.dt;
+  TO *cstage = stage + c * Ps::PER_C;
+#pragma nv_diag_suppress 549                  // every chain is initialised at its birth step (k = j + 1) before use
+  CarChain<T> ch[NJ > 0 ? NJ : 1];
+  static_for<J0 + 1, S + 1>([&](auto kc) {
+    constexpr int k = decltype(kc)::value;
+    // chains of this pass that are alive at state k: J0 <= j <= min(k-2, J1-1)
+    constexpr int JE = (k - 1 < J1) ? (k - 1) : J1;          // exclusive end
+    constexpr bool ALIVE = JE > J0;
+    T nhx = T(0), nhy = T(0);
+    if constexpr (ALIVE) {
+      nhx = geo[0][k][si]; nhy = geo[1][k][si];
+      // row k of the sample: d g_k / d u_{j,c} = -n_k . rho_k^{(j,c)}
+      static_for<J0, JE>([&](auto jc) {
+        constexpr int j = decltype(jc)::value;
+        cstage[Ps::pre(J0, j) + si * CarCol<S, j>::STRIDE + (k - j - 2)] =
+            (TO)(-fma(nhx, ch[j - J0].rx, nhy * ch[j - J0].ry));
+      });
+    }
+    if constexpr (k < S) {
+      const T ttx = E.tt[c][k][0], tty = E.tt[c][k][1];
+      if constexpr (ALIVE) {
+        const T om_n = geo[2][k][si];
+        const T g11 = -om_n * fma(-nhx, nhx, T(1)), g12 = om_n * nhx * nhy,
+                g22 = -om_n * fma(-nhy, nhy, T(1));           // dt * dF/dp_ego
+        static_for<J0, JE>([&](auto jc) {
+          constexpr int j = decltype(jc)::value;
+          CarChain<T> &h = ch[j - J0];
+          const T sy = wsdt * h.wy;
+          const T nwx = fma(g11, h.rx, fma(g12, h.ry, h.wx - sy));
+          const T nwy = fma(g12, h.rx, fma(g22, h.ry, h.wy - sy));
+          h.rx = fma(-dt, h.wx, h.rx + ttx);
+          h.ry = fma(-dt, h.wy, h.ry + tty);
+          h.wx = nwx; h.wy = nwy;
+        });
+      }
+      // chain j = k-1 is born at this step: rho_{k+1} = T_c(k), w_{k+1} = 0
+      if constexpr (k - 1 >= J0 && k - 1 < J1) {
+        ch[k - 1 - J0].rx = ttx; ch[k - 1 - J0].ry = tty; ch[k - 1 - J0].wx = T(0); ch[k - 1 - J0].wy = T(0);
+      }
+    }
+  });
+}
+
+template <typename T, typename TO, int S, int P>
+__device__ __forceinline__ void car_passes(const CarArgs<T, TO, S> &A, const CarEgo<T, S> &E,
+                                           const T (*geo)[S + 1][kTileSamples], TO *stage, int c, int si,
+                                           int lane, i64 s0, int ns, T wsdt) {
+  using Ps = CarPass<S, SAA_CAR_CAP>;
+  if constexpr (P < Ps::NPASS) {
     constexpr int J0 = Ps::bound(P), J1 = Ps::bound(P + 1);
-    T zmax;
-    car_pass<T, S, J0, J1, P == 0>(A, E, stage, c, si, qx, qy, wx, wy, w_s, w_r, dwx, dwy, zmax);
-    if (P == 0 && A.Z != nullptr && c == 0 && active) A.Z[s] = zmax - A.ztol;
+    car_chain_pass<T, TO, S, J0, J1>(A, E, geo, stage, c, si, wsdt);
     __syncwarp();
-    if (P == 0 && A.ub != nullptr)
-      copy_run<T, S, (S | 1)>(A.ub + A.ub_off + s0 * S, stage + Ps::UB, ns * S, lane);
-    car_copy_cols<T, S, J0, J0, J1>(A, stage, s0 + A.first_out, ns, lane);
+    car_copy_cols<T, TO, S, J0, J0, J1>(A, stage, s0 + A.first_out, ns, lane);
     __syncwarp();
-    car_passes<T, S, P + 1>(A, E, stage, c, si, lane, s, s0, ns, active, qx, qy, wx, wy, w_s, w_r, dwx, dwy);
+    car_passes<T, TO, S, P + 1>(A, E, geo, stage, c, si, lane, s0, ns, wsdt);
   }
 }
 
 // ---- K2: linearize + assemble ---------------------------------------------------
-template <typename T, int S, int WARPS>
+template <typename T, typename TO, int S, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1)
-car_assemble_kernel(const __grid_constant__ CarArgs<T, S> A) {
+car_assemble_kernel(const __grid_constant__ CarArgs<T, TO, S> A) {
+  using Ps = CarPass<S, SAA_CAR_CAP>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  auto &sm = *reinterpret_cast<CarSmem<T, S, WARPS> *>(smem_raw);
+  auto &sm = *reinterpret_cast<CarSmem<T, TO, S, WARPS> *>(smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = lane >> 4, si = lane & 15;
   if (threadIdx.x == 0) car_ego_rollout<T, S>(A.us, A.ego0, A.dt, sm.ego);
   __syncthreads();
-  if (blockIdx.x == 0 && A.sums != nullptr) car_final_rows<T, S>(A, sm.ego, threadIdx.x, WARPS * 32);
+  if (blockIdx.x == 0 && A.sums != nullptr) car_final_rows<T, TO, S>(A, sm.ego, threadIdx.x, WARPS * 32);
   if (A.Ax == nullptr) return;              // relaxed iteration: only the final rows are needed
   const CarEgo<T, S> &E = sm.ego;
-  T *stage = sm.stage[warp];
+  T (*geo)[S + 1][kTileSamples] = sm.geo[warp];
+  unsigned char *stage_raw = sm.stage[warp];
+  bool bad = false;
 
   const i64 ntiles = (A.M + kTileSamples - 1) / kTileSamples;
 #pragma unroll 1
@@ -445,40 +519,47 @@ car_assemble_kernel(const __grid_constant__ CarArgs<T, S> A) {
     const int ns = (int)min((i64)kTileSamples, A.M - s0);
     const bool active = si < ns;
     const i64 s = s0 + (active ? si : 0);
-    T dwx[S], dwy[S];
-#pragma unroll
-    for (int k = 0; k < S; ++k) {
-      dwx[k] = __ldcs(A.dw + (i64)(2 * k) * A.Mpad + s);
-      dwy[k] = __ldcs(A.dw + (i64)(2 * k + 1) * A.Mpad + s);
-    }
-    const T qx = __ldcs(A.x0 + s), qy = __ldcs(A.x0 + A.Mpad + s);
-    const T wx = __ldcs(A.x0 + 2 * A.Mpad + s), wy = __ldcs(A.x0 + 3 * A.Mpad + s);
     const T w_s = __ldcs(A.om + s), w_r = __ldcs(A.om + A.Mpad + s);
-    car_passes<T, S, 0>(A, E, stage, c, si, lane, s, s0, ns, active, qx, qy, wx, wy, w_s, w_r, dwx, dwy);
+    T zmax;
+    bool tile_bad = false;
+    car_rollout_pass<T, TO, S>(A, E, geo, stage_raw, c, si, s, w_s, w_r, zmax, tile_bad);
+    bad |= tile_bad && active && c == 0;
+    if (A.Z != nullptr && c == 0 && active) A.Z[s] = (TO)(zmax - A.ztol);
+    __syncwarp();
+    if (A.ub != nullptr)
+      car_copy_run<TO, S, Ps::UBROW>(A.ub + A.ub_off + s0 * S,
+                                     reinterpret_cast<const TO *>(stage_raw + 2 * S * kTileSamples * sizeof(T)),
+                                     ns * S, lane);
+    __syncwarp();
+    car_passes<T, TO, S, 0>(A, E, geo, reinterpret_cast<TO *>(stage_raw), c, si, lane, s0, ns, w_s * A.dt);
+  }
+  if (A.nonfinite != nullptr) {
+    const unsigned m = __ballot_sync(0xffffffffu, bad);
+    if (lane == 0 && m) atomicAdd(A.nonfinite, (unsigned long long)__popc(m));
   }
 }
 
 // ---- K4 / K5: rollout only ----------------------------------------------------------
-template <typename T, int S> struct CarRollArgs {
+template <typename T, typename TO, int S> struct CarRollArgs {
   const T *x0, *om, *dw;
   i64 M, Mpad;
   T us[S * 2];
   T ego0[4];
   T dt, noise_c, v_des, d_min;
-  T *Xs;            // (M, S+1, 8) or nullptr
-  T *Z;             // (M) or nullptr
+  TO *Xs;           // (M, S+1, 8) or nullptr
+  TO *Z;            // (M) or nullptr
   T ztol, t_risk, sat_tol;
   double *partials; // [gridDim.x][3] or nullptr
 };
 
-template <typename T, int S, int WARPS>
+template <typename T, typename TO, int S, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
-car_rollout_kernel(const __grid_constant__ CarRollArgs<T, S> A) {
+car_rollout_kernel(const __grid_constant__ CarRollArgs<T, TO, S> A) {
   constexpr int ROW = (S + 1) * 8, STRIDE = ROW | 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ T ego[S + 1][4];
   __shared__ double red[WARPS][3];
-  T *stage = reinterpret_cast<T *>(smem_raw) + (threadIdx.x >> 5) * 32 * STRIDE;
+  TO *stage = reinterpret_cast<TO *>(smem_raw) + (threadIdx.x >> 5) * 32 * STRIDE;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     T px = A.ego0[0], py = A.ego0[1], v = A.ego0[2], phi = A.ego0[3];
@@ -502,7 +583,7 @@ car_rollout_kernel(const __grid_constant__ CarRollArgs<T, S> A) {
     T qx = A.x0[s], qy = A.x0[A.Mpad + s], wx = A.x0[2 * A.Mpad + s], wy = A.x0[3 * A.Mpad + s];
     const T w_s = A.om[s], w_r = A.om[A.Mpad + s];
     T zmax = -INFINITY;
-    T *mine = stage + lane * STRIDE;
+    TO *mine = stage + lane * STRIDE;
     T dwx[S], dwy[S];
 #pragma unroll
     for (int k = 0; k < S; ++k) {
@@ -513,8 +594,8 @@ car_rollout_kernel(const __grid_constant__ CarRollArgs<T, S> A) {
     for (int k = 0; k <= S; ++k) {
       if (A.Xs != nullptr) {
 #pragma unroll
-        for (int f = 0; f < 4; ++f) mine[k * 8 + f] = ego[k][f];
-        mine[k * 8 + 4] = qx; mine[k * 8 + 5] = qy; mine[k * 8 + 6] = wx; mine[k * 8 + 7] = wy;
+        for (int f = 0; f < 4; ++f) mine[k * 8 + f] = (TO)ego[k][f];
+        mine[k * 8 + 4] = (TO)qx; mine[k * 8 + 5] = (TO)qy; mine[k * 8 + 6] = (TO)wx; mine[k * 8 + 7] = (TO)wy;
       }
       const T dx = ego[k][0] - qx, dy = ego[k][1] - qy;
       const T n2 = fma(dx, dx, dy * dy);
@@ -530,7 +611,7 @@ car_rollout_kernel(const __grid_constant__ CarRollArgs<T, S> A) {
       }
     }
     const T Zi = zmax - A.ztol;
-    if (A.Z != nullptr && active) A.Z[s] = Zi;
+    if (A.Z != nullptr && active) A.Z[s] = (TO)Zi;
     if (active) {
       acc_excess += (double)fmax(Zi - A.t_risk, T(0));
       acc_sat += (Zi <= A.sat_tol) ? 1.0 : 0.0;
@@ -538,7 +619,7 @@ car_rollout_kernel(const __grid_constant__ CarRollArgs<T, S> A) {
     }
     if (A.Xs != nullptr) {
       __syncwarp();
-      copy_run<T, ROW, STRIDE>(A.Xs + s0 * ROW, stage, ns * ROW, lane);
+      copy_run<TO, ROW, STRIDE>(A.Xs + s0 * ROW, stage, ns * ROW, lane);
       __syncwarp();
     }
   }

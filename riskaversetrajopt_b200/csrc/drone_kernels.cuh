@@ -58,7 +58,7 @@ template <int S> struct DroneRed {
 // rows of the factored trajectory record per (axis): p_1..p_S, then the 3 scaled Q entries
 template <int S> struct DroneFac { static constexpr int ROWS = S + 3; };
 
-template <typename T, int S> struct DroneArgs {
+template <typename T, typename TO, int S> struct DroneArgs {
   const T *mass, *dw, *q;   // packed: mass[M]; dw[(k*3+a)*Mpad+s]; q[(o*2+a)*Mpad+s]
   i64 M, Mpad;
   T us[S * 3];
@@ -68,18 +68,18 @@ template <typename T, int S> struct DroneArgs {
   T escale;                 // multiplier (x relaxation scale) applied to the Jacobian entries
   T ubscale, ubpad;         // upper bound = ubscale * (-g + grad g . u) - ubpad
   T ztol;                   // Z_i = max g - ztol
-  T *Ax;
+  TO *Ax;                  // TO = storage type of the outputs (double | float); T = arithmetic type
   // Sub-run of local sample 0 in u column (j, a): Ax + CA(j,a) + M_out*CB(j,a) + first_out*LEN(j)
   // with compile-time CA, CB (DroneChain); the host checks them against Layout::run_start.
   i64 M_out, first_out;
-  T *ub;                    // base of the upper-bound vector (nullptr: skip)
+  TO *ub;                   // base of the upper-bound vector (nullptr: skip)
   i64 ub_off;               // row of local sample 0's first sample row
-  T *Z;                     // per-sample max constraint (nullptr: skip)
+  TO *Z;                    // per-sample max constraint (nullptr: skip)
   double *partials;         // [gridDim.x][DroneRed<S>::N]
   // factored record (FACTOR writes, EXPAND reads), laid out for M_out samples:
   //   fsp[M_out * FB(j,a) + sample * (S-1-j) + kk] = d p_{j+2+kk} / d u_{j,a}
   //   fp[(a * (S+3) + r) * M_out + sample]         = p_{r+1} (r < S) | -2 escale Q_o,aa (r = S+o)
-  T *fsp, *fp;
+  TO *fsp, *fp;
   i64 s_begin;              // EXPAND: first sample (of the M_out geometry) to expand; M = count
 };
 
@@ -136,11 +136,11 @@ __device__ __forceinline__ void drone_flush(T *base, T *stg, i64 g0x, i64 g0y, i
 }
 
 // ---- sensitivity chains, one CSC column pair (x and y column of control step J) per pass ----
-template <typename T, int S, int J, int MODE>
-__device__ __forceinline__ void drone_chains(const DroneArgs<T, S> &A, const DroneOut<T> &O,
+template <typename T, typename TO, int S, int J, int MODE>
+__device__ __forceinline__ void drone_chains(const DroneArgs<T, TO, S> &A, const DroneOut<TO> &O,
                                              const T (&P)[S + 1], const T (&A22)[S],
                                              const T (&q2)[3], const T (&oca)[3], T a21, T dtm,
-                                             T *stage, double *wacc, int a, int si, int lane, i64 s0,
+                                             TO *stage, double *wacc, int a, int si, int lane, i64 s0,
                                              int ns, bool active) {
   using Rd = DroneRed<S>;
   if constexpr (J >= S - 1) {
@@ -152,13 +152,13 @@ __device__ __forceinline__ void drone_chains(const DroneArgs<T, S> &A, const Dro
   } else {
     using C = DroneChain<S, J>;
     constexpr int SLEN = (MODE == DRONE_FACTOR) ? C::L : C::LEN;   // staged values per sample
-    using St = Stager<T, SLEN>;
-    static_assert(St::SIZE <= DroneSmem<T, S, 1>::HALF, "staging buffer too small");
+    using St = Stager<TO, SLEN>;
+    static_assert(St::SIZE <= DroneSmem<TO, S, 1>::HALF, "staging buffer too small");
 #if SAA_COPY == 3
     // upper bounds went through buffer 0, chain 0 takes buffer 1, chain 1 buffer 0, ...
-    T *const stg = stage + ((J & 1) ? 0 : DroneSmem<T, S, 1>::HALF);
+    TO *const stg = stage + ((J & 1) ? 0 : DroneSmem<TO, S, 1>::HALF);
 #else
-    T *const stg = stage;
+    TO *const stg = stage;
 #endif
     // optimisation barriers: keep per-chain coefficient math from being hoisted (common
     // subexpressions across the unrolled chains would cost ~60 live doubles), and recompute the
@@ -170,30 +170,30 @@ __device__ __forceinline__ void drone_chains(const DroneArgs<T, S> &A, const Dro
     opaque(sbase); opaque(mout);
     const i64 f0x = mout * C::FB0 + sbase * C::L, f0y = mout * C::FB1 + sbase * C::L;     // factored runs
     const i64 g0x = C::CA0 + mout * C::CB0 + sbase * C::LEN, g0y = C::CA1 + mout * C::CB1 + sbase * C::LEN;
-    T *mine = St::mine(stg, a, si, MODE == DRONE_FACTOR ? (a ? f0y : f0x) : (a ? g0y : g0x));
+    TO *mine = St::mine(stg, a, si, MODE == DRONE_FACTOR ? (a ? f0y : f0x) : (a ? g0y : g0x));
 #if SAA_COPY == 3
     bulk_wait_read1();             // the column pair staged two steps ago has left this buffer
     __syncwarp();
 #endif
     T sp = T(0), sv = dtm;         // d(p,v)_{J+1}/du_J = (0, dt/m)
-    const T *fin = O.fsp + (a ? f0y : f0x) + (i64)(active ? si : 0) * C::L;   // EXPAND: this sample's chain
+    const TO *fin = O.fsp + (a ? f0y : f0x) + (i64)(active ? si : 0) * C::L;   // EXPAND: this sample's chain
 #pragma unroll
     for (int k = J + 1; k < S; ++k) {
       const int kk = k - J - 1;
       if constexpr (MODE == DRONE_EXPAND) {
-        sp = fin[kk];              // d p_{k+1}/du_J computed by the rank that owns the sample
+        sp = (T)fin[kk];           // d p_{k+1}/du_J computed by the rank that owns the sample
       } else {
         const T nsp = fma(A.dt, sv, sp);
         const T nsv = fma(A22[k], sv, a21 * sp);
         sp = nsp; sv = nsv;        // now d(p,v)_{k+1} / du_J
       }
       if constexpr (MODE == DRONE_FACTOR) {
-        mine[kk] = sp;
+        mine[kk] = (TO)sp;
       } else {
 #pragma unroll
         for (int o = 0; o < 3; ++o) {
           const T coef = fma(q2j[o], P[k + 1], ocj[o]);   // escale * d g[o,k+1]/dp = q2 (p - c)
-          mine[o * C::L + kk] = coef * sp;
+          mine[o * C::L + kk] = (TO)(coef * sp);
         }
       }
     }
@@ -203,38 +203,38 @@ __device__ __forceinline__ void drone_chains(const DroneArgs<T, S> &A, const Dro
       const double rv = sum16((double)(active ? sv : T(0)));
       if (si == 0) { wacc[Rd::FIN_P + a * (S - 1) + J] += rp; wacc[Rd::FIN_V + a * S + J] += rv; }
     }
-    if constexpr (MODE == DRONE_FACTOR) drone_flush<T, SLEN>(O.fsp, stg, f0x, f0y, a, si, ns, lane);
-    else drone_flush<T, SLEN>(O.Ax, stg, g0x, g0y, a, si, ns, lane);
-    drone_chains<T, S, J + 1, MODE>(A, O, P, A22, q2, oca, a21, dtm, stage, wacc, a, si, lane, s0, ns,
+    if constexpr (MODE == DRONE_FACTOR) drone_flush<TO, SLEN>(O.fsp, stg, f0x, f0y, a, si, ns, lane);
+    else drone_flush<TO, SLEN>(O.Ax, stg, g0x, g0y, a, si, ns, lane);
+    drone_chains<T, TO, S, J + 1, MODE>(A, O, P, A22, q2, oca, a21, dtm, stage, wacc, a, si, lane, s0, ns,
                                     active);
   }
 }
 
 // ---- K1: linearize + assemble ------------------------------------------------
-template <typename T, int S, int WARPS, int MODE>
+template <typename T, typename TO, int S, int WARPS, int MODE>
 __global__ void __launch_bounds__(WARPS * 32, SAA_BPS)
-drone_assemble_kernel(const __grid_constant__ DroneArgs<T, S> A) {
+drone_assemble_kernel(const __grid_constant__ DroneArgs<T, TO, S> A) {
   using Rd = DroneRed<S>;
   constexpr int FR = DroneFac<S>::ROWS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  auto &sm = *reinterpret_cast<DroneSmem<T, S, WARPS> *>(smem_raw);
+  auto &sm = *reinterpret_cast<DroneSmem<TO, S, WARPS> *>(smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int a = lane >> 4, si = lane & 15;
-  T *stage = sm.stage[warp];
+  TO *stage = sm.stage[warp];
   double *wacc = sm.wacc[warp];
   for (int r = lane; r < Rd::N; r += 32) wacc[r] = 0.0;
   __syncwarp();
 
-  DroneOut<T> O{A.Ax, A.fsp, A.M_out, A.first_out};
+  DroneOut<TO> O{A.Ax, A.fsp, A.M_out, A.first_out};
   {
     i64 ax = (i64)O.Ax, fs = (i64)O.fsp;
     opaque(ax); opaque(fs); opaque(O.mout); opaque(O.first);
-    O.Ax = (T *)ax; O.fsp = (T *)fs;
+    O.Ax = (TO *)ax; O.fsp = (TO *)fs;
   }
   if (MODE == DRONE_EXPAND) O.first = A.s_begin;
   i64 ub_base = (i64)A.ub, ub_off = A.ub_off;
   opaque(ub_base); opaque(ub_off);
-  T *const ub_ptr = (T *)ub_base;
+  TO *const ub_ptr = (TO *)ub_base;
   const i64 ntiles = (A.M + kTileSamples - 1) / kTileSamples;
   const i64 tstride = (i64)gridDim.x * WARPS;
 #pragma unroll 1
@@ -251,11 +251,11 @@ drone_assemble_kernel(const __grid_constant__ DroneArgs<T, S> A) {
 
     if constexpr (MODE == DRONE_EXPAND) {
       // the owner of the matrix re-creates the entries of another rank's samples from the record
-      const T *fp = A.fp + (i64)a * FR * O.mout + (O.first + s);
+      const TO *fp = A.fp + (i64)a * FR * O.mout + (O.first + s);
 #pragma unroll
-      for (int k = 1; k <= S; ++k) P[k] = __ldcs(fp + (i64)(k - 1) * O.mout);
+      for (int k = 1; k <= S; ++k) P[k] = (T)__ldcs(fp + (i64)(k - 1) * O.mout);
 #pragma unroll
-      for (int o = 0; o < 3; ++o) q2[o] = __ldcs(fp + (i64)(S + o) * O.mout);
+      for (int o = 0; o < 3; ++o) q2[o] = (T)__ldcs(fp + (i64)(S + o) * O.mout);
       P[0] = T(0);
 #pragma unroll
       for (int k = 0; k < S; ++k) A22[k] = T(0);
@@ -280,9 +280,9 @@ drone_assemble_kernel(const __grid_constant__ DroneArgs<T, S> A) {
       T p = a ? A.x0[1] : A.x0[0], v = a ? A.x0[4] : A.x0[3], tp = T(0), tv = T(0);
       T zmax = -INFINITY;
       P[0] = p;
-      using StU = Stager<T, 3 * S>;
+      using StU = Stager<TO, 3 * S>;
       const i64 gu = ub_off + s0 * (3 * S);
-      T *ubrow = StU::mine(stage, 0, si, gu);
+      TO *ubrow = StU::mine(stage, 0, si, gu);
 #if SAA_COPY == 3
       bulk_wait_read1();           // buffer 0 was last used by the second-to-last column pair of the previous tile
       __syncwarp();
@@ -309,7 +309,7 @@ drone_assemble_kernel(const __grid_constant__ DroneArgs<T, S> A) {
           const T esum = e + __shfl_xor_sync(0xffffffffu, e, 16);
           zmax = fmax(zmax, T(1) - wsum);
           if (a == (k & 1))                               // the two lanes of a sample share the stores
-            ubrow[o * S + k] = fma(esum - T(1), A.ubscale, -A.ubpad);
+            ubrow[o * S + k] = (TO)fma(esum - T(1), A.ubscale, -A.ubpad);
         }
       }
       // linearisation offset of the final rows: -(x_S - x_f) + d x_S/du . u  (:271)
@@ -317,7 +317,7 @@ drone_assemble_kernel(const __grid_constant__ DroneArgs<T, S> A) {
       const double rp = sum16((double)(active ? valp : T(0)));
       const double rv = sum16((double)(active ? valv : T(0)));
       if (si == 0) { wacc[Rd::VAL + a] += rp; wacc[Rd::VAL + 3 + a] += rv; }
-      if (A.Z != nullptr && a == 0 && active) A.Z[s] = zmax - A.ztol;
+      if (A.Z != nullptr && a == 0 && active) A.Z[s] = (TO)(zmax - A.ztol);
 #if SAA_COPY == 3
       fence_async_smem();
       __syncwarp();
@@ -330,17 +330,17 @@ drone_assemble_kernel(const __grid_constant__ DroneArgs<T, S> A) {
       if constexpr (MODE == DRONE_FACTOR) {
         // trajectory part of the factored record (coalesced: 16 samples per 128-byte line)
         if (active) {
-          T *fp = A.fp + (i64)a * FR * O.mout + (O.first + s);
+          TO *fp = A.fp + (i64)a * FR * O.mout + (O.first + s);
 #pragma unroll
-          for (int k = 1; k <= S; ++k) st_stream(fp + (i64)(k - 1) * O.mout, P[k]);
+          for (int k = 1; k <= S; ++k) st_stream(fp + (i64)(k - 1) * O.mout, (TO)P[k]);
 #pragma unroll
-          for (int o = 0; o < 3; ++o) st_stream(fp + (i64)(S + o) * O.mout, q2[o]);
+          for (int o = 0; o < 3; ++o) st_stream(fp + (i64)(S + o) * O.mout, (TO)q2[o]);
         }
       }
     }
 
     // ---------------- sensitivity chains, one CSC column pair per control step -
-    drone_chains<T, S, 0, MODE>(A, O, P, A22, q2, oca, a21, dtm, stage, wacc, a, si, lane, s0, ns, active);
+    drone_chains<T, TO, S, 0, MODE>(A, O, P, A22, q2, oca, a21, dtm, stage, wacc, a, si, lane, s0, ns, active);
   }
 
 #if SAA_COPY == 3
@@ -365,9 +365,9 @@ drone_assemble_kernel(const __grid_constant__ DroneArgs<T, S> A) {
 // matrix, for the tail-reduced subproblem) runs it for all three axes.  One thread per sample:
 // rollout, then one adjoint sweep carrying e_p and e_v; the 2S+1 sums stay in registers over the
 // thread's samples and are reduced once at the end.  Reads 8 + 8S bytes per sample.
-template <typename T, int S, int WARPS>
+template <typename T, typename TO, int S, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
-drone_axis_mean_kernel(const __grid_constant__ DroneArgs<T, S> A, int axis, double *__restrict__ partials) {
+drone_axis_mean_kernel(const __grid_constant__ DroneArgs<T, TO, S> A, int axis, double *__restrict__ partials) {
   using Rd = DroneRed<S>;
   __shared__ double red[WARPS][2 * S + 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -465,27 +465,27 @@ __global__ void scatter_means_kernel(const double *__restrict__ sums, double inv
 }
 
 // ---- K4 / K5: rollout only, optional trajectory output and CVaR terms --------
-template <typename T, int S> struct DroneRollArgs {
+template <typename T, typename TO, int S> struct DroneRollArgs {
   const T *mass, *dw, *q;
   i64 M, Mpad;
   T us[S * 3];
   T dt, noise_c, drag, kp, kd;
   T x0[6];
   T oc[3][2];
-  T *Xs;            // (M, S+1, 6) or nullptr
-  T *Z;             // (M) or nullptr
+  TO *Xs;           // (M, S+1, 6) or nullptr
+  TO *Z;            // (M) or nullptr
   T ztol, t_risk, sat_tol;
   double *partials; // [gridDim.x][3] or nullptr: sum max(Z-t,0), count Z<=sat_tol, max Z
 };
 
 // one thread per sample; trajectories are staged per warp so that the
 // (S+1)*6 contiguous doubles of each sample leave as full coalesced runs.
-template <typename T, int S, int WARPS>
+template <typename T, typename TO, int S, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
-drone_rollout_kernel(const __grid_constant__ DroneRollArgs<T, S> A) {
+drone_rollout_kernel(const __grid_constant__ DroneRollArgs<T, TO, S> A) {
   constexpr int ROW = (S + 1) * 6, STRIDE = ROW | 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T *stage = reinterpret_cast<T *>(smem_raw) + (threadIdx.x >> 5) * 32 * STRIDE;
+  TO *stage = reinterpret_cast<TO *>(smem_raw) + (threadIdx.x >> 5) * 32 * STRIDE;
   __shared__ double red[WARPS][3];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double acc_excess = 0.0, acc_sat = 0.0, acc_max = -INFINITY;
@@ -504,10 +504,10 @@ drone_rollout_kernel(const __grid_constant__ DroneRollArgs<T, S> A) {
 #pragma unroll
     for (int o = 0; o < 3; ++o) { qx[o] = A.q[(o * 2) * A.Mpad + s]; qy[o] = A.q[(o * 2 + 1) * A.Mpad + s]; }
     T zmax = -INFINITY;
-    T *mine = stage + lane * STRIDE;
+    TO *mine = stage + lane * STRIDE;
     if (A.Xs != nullptr) {
 #pragma unroll
-      for (int a = 0; a < 3; ++a) { mine[a] = p[a]; mine[3 + a] = v[a]; }
+      for (int a = 0; a < 3; ++a) { mine[a] = (TO)p[a]; mine[3 + a] = (TO)v[a]; }
     }
     // all noise increments of the sample in flight at once (one DRAM round trip per tile)
     T dw[S * 3];
@@ -525,7 +525,7 @@ drone_rollout_kernel(const __grid_constant__ DroneRollArgs<T, S> A) {
       }
       if (A.Xs != nullptr) {
 #pragma unroll
-        for (int a = 0; a < 3; ++a) { mine[(k + 1) * 6 + a] = p[a]; mine[(k + 1) * 6 + 3 + a] = v[a]; }
+        for (int a = 0; a < 3; ++a) { mine[(k + 1) * 6 + a] = (TO)p[a]; mine[(k + 1) * 6 + 3 + a] = (TO)v[a]; }
       }
 #pragma unroll
       for (int o = 0; o < 3; ++o) {
@@ -534,7 +534,7 @@ drone_rollout_kernel(const __grid_constant__ DroneRollArgs<T, S> A) {
       }
     }
     const T Zi = zmax - A.ztol;
-    if (A.Z != nullptr && active) A.Z[s] = Zi;
+    if (A.Z != nullptr && active) A.Z[s] = (TO)Zi;
     if (active) {
       acc_excess += (double)fmax(Zi - A.t_risk, T(0));
       acc_sat += (Zi <= A.sat_tol) ? 1.0 : 0.0;
@@ -542,7 +542,7 @@ drone_rollout_kernel(const __grid_constant__ DroneRollArgs<T, S> A) {
     }
     if (A.Xs != nullptr) {
       __syncwarp();
-      copy_run<T, ROW, STRIDE>(A.Xs + s0 * ROW, stage, ns * ROW, lane);
+      copy_run<TO, ROW, STRIDE>(A.Xs + s0 * ROW, stage, ns * ROW, lane);
       __syncwarp();
     }
   }

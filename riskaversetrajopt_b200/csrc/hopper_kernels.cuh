@@ -28,43 +28,36 @@ namespace saa {
 constexpr int kHopperMaxContacts = 32;
 constexpr int kHopperThreads = 128;
 
-template <typename T> struct HopperArgs {
+// T = arithmetic / feature type, TO = storage type of the outputs (double | float)
+template <typename T, typename TO> struct HopperArgs {
   const T *I, *theta, *tau;   // (M, F) row-major
   i64 M;
   int F, n_c;
   int chunk;                  // samples staged per block iteration
+  int saa;                    // method == saa: rows carry - t - y_i
   T mu_nom;
-  T px[kHopperMaxContacts];
-  T *mu, *dmu;                // (M, n_c)
+  T px[kHopperMaxContacts];   // end-effector x position per contact instant (hopper.py:166-171)
+  T fx[kHopperMaxContacts], fz[kHopperMaxContacts];          // contact forces us[t, 2], us[t, 3]
+  T gp[3][kHopperMaxContacts];                               // d p / d(x0, x2, x3) = (1, x3 cos x2, sin x2)
+  T t_risk, slack;
+  const double *y;            // (M) risk variables y_i (device) or nullptr (treated as 0)
+  TO *mu, *dmu;               // (M, n_c) friction and its derivative (optional)
+  TO *g;                      // (M, n_c) slip-risk rows f_x - mu_i(p) f_z - t - y_i - slack (optional)
+  TO *jac;                    // [4][M n_c]: d row / d(x0, x2, x3, f_z) (optional)
   const double *lambda;       // (M, n_c) or nullptr
   double *w;                  // per-block partial sums [gridDim.x][2][n_c] of lambda mu', lambda mu''   (if lambda)
+  TO *Z;                      // (M) max_c (f_x - mu_i f_z) (optional; hopper.py:910-925)
+  T sat_tol;
+  double *cvar;               // per-block [gridDim.x][3]: sum max(Z - t, 0), #{Z <= sat_tol}, max Z (optional)
 };
 
-// one staged feature: 32 bytes in FP64 (two 16-byte shared loads), 16 in FP32
+// one staged feature: 32 bytes in FP64 (two 16-byte shared loads)
 template <typename T> struct __align__(4 * sizeof(T)) HopperFeat { T I, th, ta, nit; };   // nit = -I theta
 
 template <typename T, bool HESS, bool BIG>
 __device__ __forceinline__ void hopper_element(const HopperFeat<T> *row, int F, T p, T &m0, T &m1, T &m2) {
-  int f = 0;
-  if (!BIG && sizeof(T) == 4) {
-    // FP32: two features per iteration in one straight-line block (0.93 -> 0.77 ms); in FP64 ptxas
-    // serialises the two evaluations again and the plain loop below is as fast
-#pragma unroll 1
-    for (; f + 2 <= F; f += 2) {
-      const HopperFeat<T> f0 = row[f], f1 = row[f + 1];
-      const T x[2] = {fma(f0.th, p, f0.ta), fma(f1.th, p, f1.ta)};
-      T sn[2], cs[2];
-      sincos_core_n<2>(x, sn, cs);
-      m0 = fma(f0.I, cs[0], m0);
-      m1 = fma(f0.nit, sn[0], m1);
-      if (HESS) m2 = fma(f0.nit * f0.th, cs[0], m2);
-      m0 = fma(f1.I, cs[1], m0);
-      m1 = fma(f1.nit, sn[1], m1);
-      if (HESS) m2 = fma(f1.nit * f1.th, cs[1], m2);
-    }
-  }
 #pragma unroll 2
-  for (; f < F; ++f) {
+  for (int f = 0; f < F; ++f) {
     const HopperFeat<T> ft = row[f];
     const T x = fma(ft.th, p, ft.ta);
     T sn, cs;
@@ -76,13 +69,16 @@ __device__ __forceinline__ void hopper_element(const HopperFeat<T> *row, int F, 
   }
 }
 
-template <typename T, bool HESS>
+// Shared memory: [features CH x F] [HESS: 2 x CH x n_c doubles] [CVAR: CH x n_c doubles]
+template <typename T, typename TO, bool HESS, bool CVAR>
 __global__ void __launch_bounds__(kHopperThreads)
-hopper_friction_kernel(const __grid_constant__ HopperArgs<T> A) {
+hopper_friction_kernel(const __grid_constant__ HopperArgs<T, TO> A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int F = A.F, n_c = A.n_c, CH = A.chunk;
   HopperFeat<T> *sF = reinterpret_cast<HopperFeat<T> *>(smem_raw);
   double *sw = reinterpret_cast<double *>(sF + CH * F);    // HESS: [2][CH * n_c] weighted derivatives of the chunk
+  double *sc = sw + (HESS ? 2 * CH * n_c : 0);             // CVAR: [CH * n_c] constraint values of the chunk
+  __shared__ double red[kHopperThreads / 32][3];
   const i64 nchunks = (A.M + CH - 1) / CH;
   if (HESS) {
     // slot e of the chunk (a fixed (sample slot, contact) pair) is always served by the same
@@ -90,8 +86,10 @@ hopper_friction_kernel(const __grid_constant__ HopperArgs<T> A) {
     // any synchronisation; they are combined once, in a fixed order, after the last chunk
     for (int e = threadIdx.x; e < 2 * CH * n_c; e += kHopperThreads) sw[e] = 0.0;
   }
+  double acc_excess = 0.0, acc_sat = 0.0, acc_max = -INFINITY;
   T pmax = T(0);
   for (int c = 0; c < n_c; ++c) pmax = fmax(pmax, fabs(A.px[c]));
+  const i64 N = A.M * n_c;
   for (i64 chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
     const i64 i0 = chunk * CH;
     const int ns = (int)min((i64)CH, A.M - i0);
@@ -113,12 +111,37 @@ hopper_friction_kernel(const __grid_constant__ HopperArgs<T> A) {
       if (big) hopper_element<T, HESS, true>(sF + il * F, F, A.px[c], m0, m1, m2);
       else hopper_element<T, HESS, false>(sF + il * F, F, A.px[c], m0, m1, m2);
       const i64 g = i0 * n_c + e;
-      A.mu[g] = A.mu_nom + m0;
-      A.dmu[g] = m1;
+      const T mu = A.mu_nom + m0;
+      const T cons = fma(-mu, A.fz[c], A.fx[c]);       // f_x - mu_i(p) f_z  (hopper.py:318-325)
+      if (A.mu != nullptr) { A.mu[g] = (TO)mu; A.dmu[g] = (TO)m1; }
+      if (A.g != nullptr) {
+        T v = cons - A.slack;
+        if (A.saa) v = cons - A.t_risk - (A.y ? (T)A.y[i0 + il] : T(0)) - A.slack;   // :366, same order of operations
+        A.g[g] = (TO)v;
+      }
+      if (A.jac != nullptr) {
+        const T d = -A.fz[c] * m1;                     // d row / d p
+        st_stream(A.jac + g, (TO)(d * A.gp[0][c]));
+        st_stream(A.jac + N + g, (TO)(d * A.gp[1][c]));
+        st_stream(A.jac + 2 * N + g, (TO)(d * A.gp[2][c]));
+        st_stream(A.jac + 3 * N + g, (TO)(-mu));
+      }
       if (HESS) {
         const double lam = A.lambda[g];
         sw[e] += lam * (double)m1;
         sw[CH * n_c + e] += lam * (double)m2;
+      }
+      if (CVAR) sc[e] = (double)cons;
+    }
+    if (CVAR) {
+      __syncthreads();
+      for (int il = threadIdx.x; il < ns; il += kHopperThreads) {
+        double z = -INFINITY;
+        for (int c = 0; c < n_c; ++c) z = fmax(z, sc[il * n_c + c]);
+        if (A.Z != nullptr) A.Z[i0 + il] = (TO)z;
+        acc_excess += fmax(z - (double)A.t_risk, 0.0);
+        acc_sat += (z <= (double)A.sat_tol) ? 1.0 : 0.0;
+        acc_max = fmax(acc_max, z);
       }
     }
   }
@@ -132,6 +155,75 @@ hopper_friction_kernel(const __grid_constant__ HopperArgs<T> A) {
       A.w[(i64)blockIdx.x * 2 * n_c + threadIdx.x] = hacc;
     }
   }
+  if (CVAR && A.cvar != nullptr) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    acc_excess = sum32(acc_excess); acc_sat = sum32(acc_sat); acc_max = max32(acc_max);
+    if (lane == 0) { red[warp][0] = acc_excess; red[warp][1] = acc_sat; red[warp][2] = acc_max; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double e = 0.0, cc = 0.0, m = -INFINITY;
+      for (int w = 0; w < kHopperThreads / 32; ++w) { e += red[w][0]; cc += red[w][1]; m = fmax(m, red[w][2]); }
+      A.cvar[(i64)blockIdx.x * 3 + 0] = e;
+      A.cvar[(i64)blockIdx.x * 3 + 1] = cc;
+      A.cvar[(i64)blockIdx.x * 3 + 2] = m;
+    }
+  }
+}
+
+// The sample-independent rest of the slip-risk block (saa, hopper.py:350-357): row 0 =
+// M alpha t + sum_i y_i (deterministic two-level sum), rows 1 + i = -y_i, last row = 0.
+template <typename TO>
+__global__ void __launch_bounds__(256)
+hopper_head_rows_kernel(const double *__restrict__ y, i64 M, TO *__restrict__ rows_y, double *__restrict__ partials) {
+  __shared__ double red[8];
+  double acc = 0.0;
+  for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (i64)gridDim.x * blockDim.x) {
+    const double v = y[i];
+    rows_y[i] = (TO)(-v);
+    acc += v;
+  }
+  acc = sum32(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    partials[blockIdx.x] = t;
+  }
+}
+template <typename TO>
+__global__ void hopper_head_finish_kernel(const double *__restrict__ partials, int nblocks, double M_alpha_t,
+                                          TO *__restrict__ row0, TO *__restrict__ row_last) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double t = 0.0;
+    for (int b = 0; b < nblocks; ++b) t += partials[b];
+    *row0 = (TO)(M_alpha_t + t);
+    *row_last = (TO)0;
+  }
+}
+
+// Hessian of lambda . g restricted to the slip-risk rows: per contact c a symmetric block on
+// (x0, x2, x3, f_z)_t, lower triangle in the order (0,0) (1,0) (1,1) (2,0) (2,1) (2,2) (3,0) (3,1) (3,2) (3,3):
+//   -f_z (L2 grad p grad p^T + L1 Hess p) on (x0,x2,x3)^2,  -L1 grad p on (f_z, x),  0 on (f_z, f_z)
+// with L1 = sum_i lambda_ic mu_i', L2 = sum_i lambda_ic mu_i''; Hess p: (x2,x2) = -x3 sin x2, (x2,x3) = cos x2.
+__global__ void hopper_hess_blocks_kernel(const double *__restrict__ sums /* [n_c][2] */, int n_c,
+                                          const double *__restrict__ geo /* [6][n_c]: fz, gp0, gp1, gp2, h11, h12 */,
+                                          double *__restrict__ out /* [10][n_c] */) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_c) return;
+  const double L1 = sums[2 * c], L2 = sums[2 * c + 1];
+  const double fz = geo[c], g0 = geo[n_c + c], g1 = geo[2 * n_c + c], g2 = geo[3 * n_c + c];
+  const double h11 = geo[4 * n_c + c], h12 = geo[5 * n_c + c];
+  out[0 * n_c + c] = -fz * (L2 * g0 * g0);
+  out[1 * n_c + c] = -fz * (L2 * g1 * g0);
+  out[2 * n_c + c] = -fz * (L2 * g1 * g1 + L1 * h11);
+  out[3 * n_c + c] = -fz * (L2 * g2 * g0);
+  out[4 * n_c + c] = -fz * (L2 * g2 * g1 + L1 * h12);
+  out[5 * n_c + c] = -fz * (L2 * g2 * g2);
+  out[6 * n_c + c] = -L1 * g0;
+  out[7 * n_c + c] = -L1 * g1;
+  out[8 * n_c + c] = -L1 * g2;
+  out[9 * n_c + c] = 0.0;
 }
 
 // out[2c + which] = sum over blocks of partials[b][which][c]; one warp per output, lanes stride

@@ -32,11 +32,23 @@ inline int Layout::fin_rows(int c, int rows[4]) const {
 // to reach the velocity, one more to reach the position); the drone's z axis
 // never enters the planar obstacle constraint.
 inline int Layout::run_len(int c) const {
-  if (relaxed_pattern) return 0;
+  if (relaxed_pattern) return 0;     // only sample 0 may keep rows: relaxed_extra()
   const int j = c / n_u, a = c % n_u;
   if (j > S - 2) return 0;
   if (problem == SAA_DRONE && a == 2) return 0;
   return blk * (S - 1 - j);
+}
+
+// Car, scp_iter == 0 (car/driving.py:411-415): rows >= n_x = 8 are multiplied by exactly 0 and
+// vanish, rows < n_x survive untouched.  There are only n_fin = 4 final rows, so the survivors
+// are the CVaR row and the first keep_y "-y_i" rows (saa), and -- when the risk rows run out
+// before row 8 (baseline: at once; saa: M < 3) -- the first keep_s separation rows of sample 0,
+// WITH their Jacobian values.  Entries of u column (j, c) among them: steps k = j+2 .. keep_s.
+inline int Layout::relaxed_extra(int c) const {
+  if (!relaxed_pattern) return 0;
+  const int j = c / n_u;
+  const int n = keep_s - (j + 1);
+  return n > 0 ? n : 0;
 }
 
 inline i64 Layout::ycol_len() const {
@@ -59,9 +71,16 @@ inline void Layout::build(int problem_, int method_, int S_, i64 M_, bool relaxe
   }
   n_rows = row_ctrl0 + nu;
   n_cols = nu + M + 2;
+  keep_y = keep_s = 0;
+  if (relaxed_pattern) {
+    if (method == SAA_METHOD_SAA) keep_y = (int)(n_x - n_fin - 1 < M ? n_x - n_fin - 1 : M);
+    keep_s = (int)(n_x > row_s0 ? n_x - row_s0 : 0);
+    if (keep_s > S) keep_s = S;
+  }
   ucol.assign(nu + 1, 0);
   int rows[4];
-  for (int c = 0; c < nu; ++c) ucol[c + 1] = ucol[c] + fin_rows(c, rows) + M * run_len(c) + 1;
+  for (int c = 0; c < nu; ++c)
+    ucol[c + 1] = ucol[c] + fin_rows(c, rows) + M * run_len(c) + relaxed_extra(c) + 1;
   ycol0 = ucol[nu];
   if (method != SAA_METHOD_SAA) {
     slackcol = tcol = nnz = ycol0;      // y / slack / t columns are empty
@@ -72,12 +91,10 @@ inline void Layout::build(int problem_, int method_, int S_, i64 M_, bool relaxe
     tcol = slackcol + (M + 2);          // CVaR row (quirk), M rows "-y_i - slack", last row
     nnz = tcol + 1 + M * R;
   } else {
-    // car, scp_iter == 0: only rows < n_x survive = final rows, CVaR row, and
-    // the first n_x - n_fin - 1 "-y_i" rows (car/driving.py:411-415)
-    const i64 keep = n_x - n_fin - 1 < M ? n_x - n_fin - 1 : M;
-    slackcol = ycol0 + M + keep;        // each y: CVaR row; y_i, i < keep: also row n_fin+1+i
-    tcol = slackcol + 1 + keep;
-    nnz = tcol + 1;
+    // each y: CVaR row; y_i, i < keep_y: also row n_fin+1+i; y_0: sample 0's surviving rows
+    slackcol = ycol0 + M + keep_y + keep_s;
+    tcol = slackcol + 1 + keep_y;
+    nnz = tcol + 1 + keep_s;
   }
 }
 
@@ -100,6 +117,7 @@ void Layout::fill(I *indptr, I *indices) const {
       }
       out += M * len;
     }
+    for (int e = 0; e < relaxed_extra(c); ++e) *out++ = (I)(row_s0 + (j + 1 + e));   // sample 0, step j+2+e
     *out++ = (I)(row_ctrl0 + c);
   }
   if (method != SAA_METHOD_SAA) {
@@ -128,18 +146,19 @@ void Layout::fill(I *indptr, I *indices) const {
     for (i64 r = 0; r < M * R; ++r) o_[r] = (I)(row_s0 + r);
     indptr[nu + M + 2] = (I)nnz;
   } else {
-    const i64 keep = n_x - n_fin - 1 < M ? n_x - n_fin - 1 : M;
     i64 pos = ycol0;
     for (i64 i = 0; i < M; ++i) {
       indptr[nu + i] = (I)pos;
       indices[pos++] = (I)row_cvar;
-      if (i < keep) indices[pos++] = (I)(row_y0 + i);
+      if (i < keep_y) indices[pos++] = (I)(row_y0 + i);
+      if (i == 0) for (int e = 0; e < keep_s; ++e) indices[pos++] = (I)(row_s0 + e);
     }
     indptr[nu + M] = (I)pos;
     indices[pos++] = (I)row_cvar;
-    for (i64 i = 0; i < keep; ++i) indices[pos++] = (I)(row_y0 + i);
+    for (i64 i = 0; i < keep_y; ++i) indices[pos++] = (I)(row_y0 + i);
     indptr[nu + M + 1] = (I)pos;
     indices[pos++] = (I)row_cvar;
+    for (int e = 0; e < keep_s; ++e) indices[pos++] = (I)(row_s0 + e);
     indptr[nu + M + 2] = (I)pos;
   }
 }

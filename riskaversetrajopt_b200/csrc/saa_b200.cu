@@ -47,6 +47,9 @@ struct saa_handle {
   double *d_partials = nullptr; i64 partials_len = 0;
   double *d_sums = nullptr;
   i64 *d_fin_off = nullptr;          // [0..255]: normal pattern, [256..511]: car relaxed pattern
+  void *d_relax_scratch = nullptr; i64 relax_scratch_bytes = 0;   // car scp_iter 0: sample 0 alone
+  unsigned long long *d_nonfinite = nullptr;                      // samples with a non-finite rollout (saa_check_finite)
+  double *d_hopper_geo = nullptr;                                 // hopper Hessian: [6][32] contact geometry
   Layout lay;                 // destination geometry (M_out)
   mutable std::string err;
 };
@@ -64,7 +67,8 @@ int fail(const saa_handle *h, int code, const std::string &msg) {
       return fail(h, SAA_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
   } while (0)
 
-size_t esize(const saa_handle *h) { return h->precision == 64 ? 8 : 4; }
+// precision 32 = FP32 STORAGE of the outputs; the packed samples and the arithmetic stay FP64
+constexpr size_t kInSize = sizeof(double);
 
 int relax_threshold(const saa_handle *h) { return h->problem == SAA_DRONE ? 2 : 1; }
 
@@ -89,6 +93,10 @@ int ensure_scratch(saa_handle *h, i64 partial_doubles) {
     h->partials_len = partial_doubles;
   }
   if (!h->d_sums) SAA_CUDA(h, cudaMalloc(&h->d_sums, 1024 * sizeof(double)));
+  if (!h->d_nonfinite) {
+    SAA_CUDA(h, cudaMalloc(&h->d_nonfinite, sizeof(unsigned long long)));
+    SAA_CUDA(h, cudaMemset(h->d_nonfinite, 0, sizeof(unsigned long long)));
+  }
   return SAA_OK;
 }
 
@@ -262,11 +270,12 @@ i64 drone_col_start(int j, int a, int S, i64 M) {
 
 // mode: DRONE_FULL (Ax), DRONE_FACTOR (fsp/fp record instead of Ax), DRONE_EXPAND (record -> Ax for
 // samples [s_begin, s_begin + count) of the output geometry)
-template <typename T, int MODE>
+template <typename TO, int MODE>
 int launch_drone_assemble(saa_handle *h, const double *us, int scp_iter, void *Ax, void *u, void *Z,
                           void *fsp, void *fp, i64 s_begin, i64 count, double *sums, cudaStream_t st) {
-  using Args = DroneArgs<T, kS>;
-  using Smem = DroneSmem<T, kS, kWarps>;
+  using T = double;
+  using Args = DroneArgs<T, TO, kS>;
+  using Smem = DroneSmem<TO, kS, kWarps>;
   Args A{};
   A.mass = (const T *)h->d_a; A.dw = (const T *)h->d_b; A.q = (const T *)h->d_c;
   A.M = MODE == DRONE_EXPAND ? count : h->M_local; A.Mpad = h->Mpad;
@@ -278,7 +287,7 @@ int launch_drone_assemble(saa_handle *h, const double *us, int scp_iter, void *A
   const bool relaxed = scp_iter < 2;
   A.escale = (T)(relaxed ? mult * scale : mult);
   A.ubscale = (T)mult; A.ubpad = (T)pad; A.ztol = (T)0;
-  A.Ax = (T *)Ax; A.fsp = (T *)fsp; A.fp = (T *)fp; A.s_begin = s_begin;
+  A.Ax = (TO *)Ax; A.fsp = (TO *)fsp; A.fp = (TO *)fp; A.s_begin = s_begin;
   const Layout &L = h->lay;
   A.M_out = h->M_out; A.first_out = h->first_out;
   // the kernel derives the column positions in closed form; they must agree with the layout
@@ -286,9 +295,9 @@ int launch_drone_assemble(saa_handle *h, const double *us, int scp_iter, void *A
     for (int j = 0; j < kS - 1; ++j)
       if (L.run_start(j * 3 + a) != drone_col_start(j, a, kS, h->M_out))
         return fail(h, SAA_ERR_STATE, "internal: closed-form column offsets disagree with the layout");
-  A.ub = relaxed ? nullptr : (T *)u;          // relaxed: bounds are the constant +-bound
+  A.ub = relaxed ? nullptr : (TO *)u;         // relaxed: bounds are the constant +-bound
   A.ub_off = L.row_s0 + h->first_out * L.R;
-  A.Z = (T *)Z;
+  A.Z = (TO *)Z;
   const i64 ntiles = (A.M + kTileSamples - 1) / kTileSamples;
   const int grid = grid_for(h, ntiles, kWarps, kBlocksPerSM);
   // rows [0, grid) of the partial sums come from the assemble kernel, rows [grid, grid + gridz)
@@ -299,12 +308,12 @@ int launch_drone_assemble(saa_handle *h, const double *us, int scp_iter, void *A
   int rc = ensure_scratch(h, (i64)(grid + gridz) * DroneRed<kS>::N);
   if (rc) return rc;
   A.partials = h->d_partials;
-  auto kern = drone_assemble_kernel<T, kS, kWarps, MODE>;
+  auto kern = drone_assemble_kernel<T, TO, kS, kWarps, MODE>;
   SAA_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
   kern<<<grid, kWarps * 32, sizeof(Smem), st>>>(A);
   SAA_CUDA(h, cudaGetLastError());
   if (MODE == DRONE_EXPAND) return SAA_OK;
-  drone_axis_mean_kernel<T, kS, kZWarps><<<gridz, kZWarps * 32, 0, st>>>(A, 2, h->d_partials + (i64)grid * DroneRed<kS>::N);
+  drone_axis_mean_kernel<T, TO, kS, kZWarps><<<gridz, kZWarps * 32, 0, st>>>(A, 2, h->d_partials + (i64)grid * DroneRed<kS>::N);
   SAA_CUDA(h, cudaGetLastError());
   const int n = DroneRed<kS>::N;
   reduce_partials_kernel<double><<<(n + 3) / 4, 128, 0, st>>>(h->d_partials, grid + gridz, n, sums);
@@ -312,25 +321,26 @@ int launch_drone_assemble(saa_handle *h, const double *us, int scp_iter, void *A
   return SAA_OK;
 }
 
-template <typename T>
+template <typename TO>
 int launch_drone_rollout(saa_handle *h, const double *us, void *Xs, void *Z, double t_risk,
                          double sat_tol, double ztol, double *out3, cudaStream_t st) {
   constexpr int W = 4;
-  using Args = DroneRollArgs<T, kS>;
+  using T = double;
+  using Args = DroneRollArgs<T, TO, kS>;
   Args A{};
   A.mass = (const T *)h->d_a; A.dw = (const T *)h->d_b; A.q = (const T *)h->d_c;
   A.M = h->M_local; A.Mpad = h->Mpad;
   fill_drone_common<T>(h, us, A.us, A.dt, A.noise_c, A.drag, A.kp, A.kd, A.x0, A.oc);
-  A.Xs = (T *)Xs; A.Z = (T *)Z;
+  A.Xs = (TO *)Xs; A.Z = (TO *)Z;
   A.ztol = (T)ztol; A.t_risk = (T)t_risk; A.sat_tol = (T)sat_tol;
   const i64 ntiles = (h->M_local + 31) / 32;
   const int grid = grid_for(h, ntiles, W, 4);
   int rc = ensure_scratch(h, (i64)grid * 3);
   if (rc) return rc;
   A.partials = out3 ? h->d_partials : nullptr;
-  const size_t smem = Xs ? (size_t)W * 32 * (((kS + 1) * 6) | 1) * sizeof(T) : 0;
-  auto kern = drone_rollout_kernel<T, kS, W>;
-  SAA_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(W * 32 * (((kS + 1) * 6) | 1) * sizeof(T))));
+  const size_t smem = Xs ? (size_t)W * 32 * (((kS + 1) * 6) | 1) * sizeof(TO) : 0;
+  auto kern = drone_rollout_kernel<T, TO, kS, W>;
+  SAA_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(W * 32 * (((kS + 1) * 6) | 1) * sizeof(TO))));
   kern<<<grid, W * 32, smem, st>>>(A);
   SAA_CUDA(h, cudaGetLastError());
   if (out3) {
@@ -450,7 +460,8 @@ int saa_destroy(saa_handle *h) {
   if (!h) return SAA_OK;
   cudaSetDevice(h->device);
   cudaFree(h->d_a); cudaFree(h->d_b); cudaFree(h->d_c); cudaFree(h->d_d);
-  cudaFree(h->d_partials); cudaFree(h->d_sums); cudaFree(h->d_fin_off);
+  cudaFree(h->d_partials); cudaFree(h->d_sums); cudaFree(h->d_fin_off); cudaFree(h->d_relax_scratch);
+  cudaFree(h->d_nonfinite); cudaFree(h->d_hopper_geo);
   delete h;
   return SAA_OK;
 }
@@ -471,21 +482,23 @@ int saa_set_samples_drone(saa_handle *h, const double *masses, const double *DWs
   SAA_CUDA(h, cudaSetDevice(h->device));
   const i64 M = h->M_local;
   h->Mpad = (M + kTileSamples - 1) / kTileSamples * kTileSamples;
-  const size_t es = esize(h);
+  const size_t es = kInSize;
   if (!h->d_a) {
-    SAA_CUDA(h, cudaMalloc(&h->d_a, h->Mpad * es));
-    SAA_CUDA(h, cudaMalloc(&h->d_b, h->Mpad * es * 3 * h->S));
-    SAA_CUDA(h, cudaMalloc(&h->d_c, h->Mpad * es * 6));
+    void *a = nullptr, *b = nullptr, *c = nullptr;       // commit to the handle only if all succeed
+    cudaError_t e = cudaMalloc(&a, h->Mpad * es);
+    if (e == cudaSuccess) e = cudaMalloc(&b, h->Mpad * es * 3 * h->S);
+    if (e == cudaSuccess) e = cudaMalloc(&c, h->Mpad * es * 6);
+    if (e != cudaSuccess) {
+      cudaFree(a); cudaFree(b); cudaFree(c);
+      return fail(h, SAA_ERR_CUDA, std::string("cudaMalloc (packed samples): ") + cudaGetErrorString(e));
+    }
+    h->d_a = a; h->d_b = b; h->d_c = c;
   }
   const int threads = 128;
   const int blocks = (int)((h->Mpad + threads - 1) / threads);
   cudaStream_t st = (cudaStream_t)stream;
-  if (h->precision == 64)
-    drone_pack_kernel<double><<<blocks, threads, 0, st>>>(masses, DWs, obs_Qs, M, h->Mpad, h->S,
-                                                        (double *)h->d_a, (double *)h->d_b, (double *)h->d_c);
-  else
-    drone_pack_kernel<float><<<blocks, threads, 0, st>>>(masses, DWs, obs_Qs, M, h->Mpad, h->S,
-                                                       (float *)h->d_a, (float *)h->d_b, (float *)h->d_c);
+  drone_pack_kernel<double><<<blocks, threads, 0, st>>>(masses, DWs, obs_Qs, M, h->Mpad, h->S,
+                                                      (double *)h->d_a, (double *)h->d_b, (double *)h->d_c);
   SAA_CUDA(h, cudaGetLastError());
   h->samples_set = true;
   return SAA_OK;
@@ -719,10 +732,26 @@ int saa_rollout(saa_handle *h, const double *us, void *Xs, void *stream) {
                             : launch_car_rollout<float>(h, us, Xs, nullptr, 0, 0, 0, nullptr, st);
 }
 
+int saa_check_finite(saa_handle *h, int64_t *count_out, void *stream) {
+  if (!h) return fail(h, SAA_ERR_ARG, "NULL handle");
+  SAA_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = ensure_scratch(h, 1);
+  if (rc) return rc;
+  unsigned long long n = 0;
+  SAA_CUDA(h, cudaMemcpyAsync(&n, h->d_nonfinite, sizeof(n), cudaMemcpyDeviceToHost, st));
+  SAA_CUDA(h, cudaMemsetAsync(h->d_nonfinite, 0, sizeof(n), st));
+  SAA_CUDA(h, cudaStreamSynchronize(st));
+  if (count_out) *count_out = (int64_t)n;
+  if (n) return fail(h, SAA_ERR_NONFINITE, std::to_string(n) + " sample(s) met a zero / non-finite ego-pedestrian distance "
+                                           "(car/driving.py:154 divides by it): their rows are NaN");
+  return SAA_OK;
+}
+
 int saa_cvar_terms(saa_handle *h, const double *us, double t_risk, double sat_tol, void *Z,
                    double *out3, void *stream) {
   if (!h || !us || !out3) return fail(h, SAA_ERR_ARG, "NULL argument");
-  if (h->problem == SAA_HOPPER) return fail(h, SAA_ERR_ARG, "use saa_hopper_friction for the hopper");
+  if (h->problem == SAA_HOPPER) return fail(h, SAA_ERR_ARG, "use saa_hopper_cvar_terms for the hopper");
   if (!h->params_set || !h->samples_set) return fail(h, SAA_ERR_STATE, "set params and samples first");
   SAA_CUDA(h, cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;

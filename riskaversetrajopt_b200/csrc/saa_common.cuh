@@ -26,6 +26,7 @@ struct Layout {
   int R = 0;            // sample rows per sample = blk * S
   i64 M = 0;            // samples in the destination matrix
   bool relaxed_pattern = false;   // car scp_iter == 0: rows >= n_x vanish
+  int keep_y = 0, keep_s = 0;     // relaxed pattern: surviving "-y_i" rows / sample-0 rows (layout.cuh)
   // rows
   i64 row_cvar = -1, row_y0 = -1, row_s0 = 0, row_slack = -1, row_ctrl0 = 0, n_rows = 0;
   // columns
@@ -38,6 +39,7 @@ struct Layout {
   int fin_rows(int c, int rows[4]) const;
   // sample-run length per sample in u column c (0 if the column carries no sample rows)
   int run_len(int c) const;
+  int relaxed_extra(int c) const;   // relaxed pattern: surviving sample-0 entries of u column c
   i64 run_start(int c) const { int r[4]; return ucol[c] + fin_rows(c, r); }
   i64 ycol_len() const;   // entries per y column
   void build(int problem_, int method_, int S_, i64 M_, bool relaxed_pattern_);

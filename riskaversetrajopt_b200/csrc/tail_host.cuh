@@ -4,9 +4,10 @@ namespace {
 
 // Expectation rows and Z_i of ALL local samples without touching the matrix: the three per-axis
 // mean kernels (drone) or the sample-independent final rows (car), plus the rollout kernel for Z.
-template <typename T>
+template <typename TO>
 int launch_drone_means(saa_handle *h, const double *us, void *Z, double *sums, cudaStream_t st) {
-  using Args = DroneArgs<T, kS>;
+  using T = double;
+  using Args = DroneArgs<T, TO, kS>;
   Args A{};
   A.mass = (const T *)h->d_a; A.dw = (const T *)h->d_b; A.q = (const T *)h->d_c;
   A.M = h->M_local; A.Mpad = h->Mpad;
@@ -18,12 +19,12 @@ int launch_drone_means(saa_handle *h, const double *us, void *Z, double *sums, c
   int rc = ensure_scratch(h, (i64)3 * gridz * n);
   if (rc) return rc;
   for (int axis = 0; axis < 3; ++axis) {
-    drone_axis_mean_kernel<T, kS, kZWarps><<<gridz, kZWarps * 32, 0, st>>>(A, axis, h->d_partials + (i64)axis * gridz * n);
+    drone_axis_mean_kernel<T, TO, kS, kZWarps><<<gridz, kZWarps * 32, 0, st>>>(A, axis, h->d_partials + (i64)axis * gridz * n);
     SAA_CUDA(h, cudaGetLastError());
   }
   reduce_partials_kernel<double><<<(n + 3) / 4, 128, 0, st>>>(h->d_partials, 3 * gridz, n, sums);
   SAA_CUDA(h, cudaGetLastError());
-  if (Z) return launch_drone_rollout<T>(h, us, nullptr, Z, 0.0, 0.0, 0.0, nullptr, st);
+  if (Z) return launch_drone_rollout<TO>(h, us, nullptr, Z, 0.0, 0.0, 0.0, nullptr, st);
   return SAA_OK;
 }
 
@@ -53,19 +54,25 @@ int launch_select(saa_handle *h, const void *Z, i64 K, i64 *idx_out, cudaStream_
   return SAA_OK;
 }
 
-template <typename T>
 int launch_gather(saa_handle *dst, const saa_handle *src, const i64 *idx, cudaStream_t st) {
+  using T = double;                                              // the packed samples are always double
   const i64 K = dst->M_local;
   const int S = src->S;
   const int rows_a = src->problem == SAA_DRONE ? 1 : 4;        // mass | pedestrian initial state
   const int rows_b = src->problem == SAA_DRONE ? 3 * S : 2;    // dw   | omegas
   const int rows_c = src->problem == SAA_DRONE ? 6 : 2 * S;    // Q    | dw
   dst->Mpad = (K + kTileSamples - 1) / kTileSamples * kTileSamples;
-  const size_t es = esize(dst);
+  const size_t es = kInSize;
   if (!dst->d_a) {
-    SAA_CUDA(dst, cudaMalloc(&dst->d_a, dst->Mpad * es * rows_a));
-    SAA_CUDA(dst, cudaMalloc(&dst->d_b, dst->Mpad * es * rows_b));
-    SAA_CUDA(dst, cudaMalloc(&dst->d_c, dst->Mpad * es * rows_c));
+    void *a = nullptr, *b = nullptr, *c = nullptr;               // commit only if all succeed
+    cudaError_t e = cudaMalloc(&a, dst->Mpad * es * rows_a);
+    if (e == cudaSuccess) e = cudaMalloc(&b, dst->Mpad * es * rows_b);
+    if (e == cudaSuccess) e = cudaMalloc(&c, dst->Mpad * es * rows_c);
+    if (e != cudaSuccess) {
+      cudaFree(a); cudaFree(b); cudaFree(c);
+      return fail(dst, SAA_ERR_CUDA, std::string("cudaMalloc (gathered samples): ") + cudaGetErrorString(e));
+    }
+    dst->d_a = a; dst->d_b = b; dst->d_c = c;
   }
   const int blocks = (int)((dst->Mpad + 255) / 256);
   gather_rows_kernel<T><<<blocks, 256, 0, st>>>((const T *)src->d_a, src->Mpad, (T *)dst->d_a, dst->Mpad, rows_a, idx, K);
@@ -117,8 +124,7 @@ int saa_gather_samples(saa_handle *dst, const saa_handle *src, const int64_t *id
   if (dst->M_local > src->M_local) return fail(dst, SAA_ERR_ARG, "destination holds more samples than the source");
   SAA_CUDA(dst, cudaSetDevice(dst->device));
   cudaStream_t st = (cudaStream_t)stream;
-  return dst->precision == 64 ? launch_gather<double>(dst, src, (const i64 *)idx, st)
-                              : launch_gather<float>(dst, src, (const i64 *)idx, st);
+  return launch_gather(dst, src, (const i64 *)idx, st);
 }
 
 }  // extern "C"

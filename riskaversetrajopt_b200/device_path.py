@@ -287,6 +287,16 @@ class DevicePath:
         A = sp.csc_matrix((data, indices, indptr), shape=(n_rows, n_cols), copy=False)
         return A, l, u
 
+    def check_finite(self, raise_error=True):
+        """Samples whose rollout met a zero / non-finite ego-pedestrian distance since the last call
+        (the car divides by it, car/driving.py:154; the reference silently returns NaN rows).
+        Synchronises the stream.  -> count; raises ``SaaError`` if non-zero and ``raise_error``."""
+        n = C.c_int64()
+        rc = lib.saa_check_finite(self._h, C.byref(n), self._stream())
+        if rc != 0 and (raise_error or n.value == 0):
+            check(rc, self._h)
+        return n.value
+
     # -- rollout / CVaR terms ---------------------------------------------------------
     def rollout(self, us_mat):
         us = self._us(us_mat)

@@ -165,6 +165,12 @@ class ShardedAssembler:
     # -- one SCP iteration ---------------------------------------------------------------
     def step(self, us_mat, scp_iter):
         p = self.path
+        if p._uses_relaxed_pattern(scp_iter):
+            # car, scp_iter 0 (car/driving.py:411-415): every sample row is multiplied by 0, so there
+            # are no row blocks to shard or gather -- the O(1)-sized problem is assembled by one rank.
+            # The buffers and merge offsets of this class are those of the normal pattern.
+            raise ValueError("car scp_iter 0 has no sample rows to shard: assemble it on one rank "
+                             "(Model.get_constraints_coeffs / DevicePath.assemble)")
         us = broadcast_controls(us_mat, 0, self.group, device=p.device if dist.get_backend(self.group) == 'nccl' else None)
         if self.mode == 'factored' and self.rank != 0:
             # constants of this rank's sample slice (remote, once per relaxation state), then the

@@ -116,6 +116,18 @@ class Model:
         px = x0 + x3 * np.sin(x2)
         return px, us[t, 2], us[t, 3], x2, x3
 
+    def _point(self, Z):
+        """``saa_hopper_point`` of the decision vector: the O(n_c) contact geometry (host)."""
+        Z = np.asarray(Z, dtype=np.float64)
+        px, fx, fz, x2, x3 = self._contact_geometry(Z)
+        _, _, _, islack, it = self._idx()
+        pt = _lib.HopperPoint()
+        pt.n_c = self.n_c
+        for name, arr in (("px", px), ("fx", fx), ("fz", fz), ("x2", x2), ("x3", x3)):
+            getattr(pt, name)[:self.n_c] = [float(v) for v in arr]
+        pt.t_risk, pt.slack = float(Z[it]), float(Z[islack])
+        return pt
+
     def _friction(self, px, lam=None):
         """Device evaluation: mu, mu' (M, n_c) and, with multipliers, the per-contact sums
         sum_i lam_ic mu_i', sum_i lam_ic mu_i''."""
@@ -133,21 +145,22 @@ class Model:
         hs = None if lam is None else self._hs.cpu().numpy().reshape(self.n_c, 2)
         return mu, dmu, hs
 
-    # ---- values: reference slip_risk_constraints (:300-367) ---------------------------
-    def slip_risk_constraints(self, Z):
+    # ---- values: reference slip_risk_constraints (:300-367), assembled on the device ----
+    def slip_risk_constraints_device(self, Z):
+        """-> device tensor (n_rows,) in the handle's storage precision."""
         Z = np.asarray(Z, dtype=np.float64)
-        px, fx, fz, _, _ = self._contact_geometry(Z)
-        mu, _, _ = self._friction(px)
-        cons = fx[None, :] - mu * fz[None, :]                         # (M, n_c)
-        _, _, iy0, islack, it = self._idx()
-        ys, slack, t_risk = Z[iy0:iy0 + self.M], Z[islack], Z[it]
-        if self.method == 'baseline':
-            return (cons - slack).reshape(-1)
-        gs = np.zeros(self.n_rows)
-        gs[0] = (self.M * self.alpha) * t_risk + np.sum(ys)
-        gs[1:1 + self.M] = -ys
-        gs[1 + self.M:1 + self.M + self.M * self.n_c] = (cons - t_risk - ys[:, None] - slack).reshape(-1)
-        return gs
+        pt = self._point(Z)
+        _, _, iy0, _, _ = self._idx()
+        y = None
+        if self.method == 'saa':
+            y = torch.as_tensor(np.ascontiguousarray(Z[iy0:iy0 + self.M])).to(self.device)
+        g = torch.empty(self.n_rows, dtype=_TORCH_DT[self.bits], device=self.device)
+        check(lib.saa_hopper_g(self._h, C.byref(pt), None if y is None else y.data_ptr(), g.data_ptr(),
+                               self._stream()), self._h)
+        return g
+
+    def slip_risk_constraints(self, Z):
+        return self.slip_risk_constraints_device(Z).cpu().numpy().astype(np.float64)
 
     # ---- Jacobian: the rows jacrev(g) holds for this block (:568-569) -------------------
     def _build_structure(self):
@@ -170,51 +183,73 @@ class Model:
             rows.append(1 + i); cols.append(iy0 + i)                              # rows 1+i: -1
         self.jac_rows = np.concatenate(rows).astype(np.int64)
         self.jac_cols = np.concatenate(cols).astype(np.int64)
+        # constant part of the values (everything but the four iterate-dependent arrays)
+        N = M_ * nc
+        consts = [np.ones(N), None, -np.ones(N)]            # d/df_x, (d/df_z: varying), d/dslack
+        if self.method == 'saa':
+            consts += [-np.ones(N), -np.ones(N), np.ones(M_), np.array([M_ * self.alpha]), -np.ones(M_)]
+        self._jac_consts = consts
+        self._jac_dev = torch.empty(4 * N, dtype=_TORCH_DT[self.bits], device=self.device)
+        self._hess_dev = torch.empty(10 * nc, dtype=torch.float64, device=self.device)
+
+    def slip_risk_jacobian_device(self, Z):
+        """-> device tensor [4][M n_c]: d row / d(x0, x2, x3, f_z) of the sample rows (the entries
+        that depend on the iterate; ``saa_hopper_jac``)."""
+        pt = self._point(Z)
+        check(lib.saa_hopper_jac(self._h, C.byref(pt), self._jac_dev.data_ptr(), self._stream()), self._h)
+        return self._jac_dev
 
     def slip_risk_jacobian(self, Z):
         """-> (rows, cols, vals): COO triplets of d(slip_risk_constraints)/dZ.  rows/cols are
         static (``self.jac_rows``, ``self.jac_cols``)."""
-        M_, nc = self.M, self.n_c
-        px, fx, fz, x2, x3 = self._contact_geometry(Z)
-        mu, dmu, _ = self._friction(px)
-        dpdx = np.stack([np.ones(nc), x3 * np.cos(x2), np.sin(x2)], axis=0)      # (3, n_c)
-        v = np.empty((5, M_, nc))
-        v[0:3] = -(fz[None, :] * dmu)[None] * dpdx[:, None, :]
-        v[3] = 1.0
-        v[4] = -mu
-        vals = [v.ravel(), -np.ones(M_ * nc)]
-        if self.method == 'saa':
-            vals += [-np.ones(M_ * nc), -np.ones(M_ * nc), np.ones(M_), np.array([M_ * self.alpha]),
-                     -np.ones(M_)]
+        N = self.M * self.n_c
+        v = self.slip_risk_jacobian_device(Z).cpu().numpy().astype(np.float64).reshape(4, N)
+        c = self._jac_consts
+        vals = [v[0], v[1], v[2], c[0], v[3]] + c[2:]
         return self.jac_rows, self.jac_cols, np.concatenate(vals)
 
     # ---- Hessian of lambda . g restricted to this block (:571-575) ----------------------
     def slip_risk_hessian(self, Z, lagrange):
         """``lagrange``: multipliers of this block's rows (length n_rows).
         -> (rows, cols, vals) of the symmetric Hessian contribution, lower triangle
-        (rows >= cols), 10 entries per contact instant."""
+        (rows >= cols), 10 entries per contact instant, formed on the device (``saa_hopper_hess``)."""
         M_, nc = self.M, self.n_c
         lagrange = np.asarray(lagrange, dtype=np.float64)
         r0 = 0 if self.method == 'baseline' else 1 + M_
-        lam = lagrange[r0:r0 + M_ * nc]
-        px, fx, fz, x2, x3 = self._contact_geometry(Z)
-        _, _, hs = self._friction(px, lam)
-        L1, L2 = hs[:, 0], hs[:, 1]                   # sum_i lam mu', sum_i lam mu''
+        lam = torch.as_tensor(np.ascontiguousarray(lagrange[r0:r0 + M_ * nc])).to(self.device)
+        pt = self._point(Z)
+        check(lib.saa_hopper_hess(self._h, C.byref(pt), lam.data_ptr(), self._hess_dev.data_ptr(),
+                                  self._stream()), self._h)
+        vals = self._hess_dev.cpu().numpy()
         ix, iu, *_ = self._idx()
         t = CONTACT_STEPS
         var = np.stack([ix(t, 0), ix(t, 2), ix(t, 3), iu(t, 3)], axis=0)       # (4, n_c): x0, x2, x3, f_z
-        gp = np.stack([np.ones(nc), x3 * np.cos(x2), np.sin(x2)], axis=0)      # grad p
-        Hp = np.zeros((3, 3, nc))
-        Hp[1, 1] = -x3 * np.sin(x2)
-        Hp[1, 2] = Hp[2, 1] = np.cos(x2)
-        H = np.zeros((4, 4, nc))
-        H[:3, :3] = -fz * (L2 * gp[:, None, :] * gp[None, :, :] + L1 * Hp)
-        H[:3, 3] = H[3, :3] = -L1 * gp
-        rows, cols, vals = [], [], []
+        rows, cols = [], []
         for a in range(4):
             for b in range(a + 1):
-                rows.append(var[a]); cols.append(var[b]); vals.append(H[a, b])
-        return np.concatenate(rows), np.concatenate(cols), np.concatenate(vals)
+                rows.append(var[a]); cols.append(var[b])
+        return np.concatenate(rows), np.concatenate(cols), vals
+
+    # ---- Monte-Carlo verification (:910-925, :957) ------------------------------------------
+    def monte_carlo_constraints(self, Z, t_risk=None, sat_tol=1e-6):
+        """-> (B_satisfied (M,), max_constraint (M,), out3) of ``no_slip_constraints_verification``
+        vmapped over this model's samples at the trajectory in ``Z``; out3 = [sum max(Z_i - t, 0),
+        #{Z_i <= sat_tol}, max Z_i] with t = ``t_risk`` (default: Z's t)."""
+        pt = self._point(Z)
+        if t_risk is not None:
+            pt.t_risk = float(t_risk)
+        Zi = torch.empty(self.M, dtype=_TORCH_DT[self.bits], device=self.device)
+        out3 = torch.empty(3, dtype=torch.float64, device=self.device)
+        check(lib.saa_hopper_cvar_terms(self._h, C.byref(pt), float(sat_tol), Zi.data_ptr(), out3.data_ptr(),
+                                        self._stream()), self._h)
+        Zh = Zi.cpu().numpy().astype(np.float64)
+        return Zh <= sat_tol, Zh, out3.cpu().numpy()
+
+    def monte_carlo_avar(self, Z, t_risk, alpha=None):
+        """t + mean(max(Z_i - t, 0)) / alpha (closed form at :957)."""
+        alpha = self.alpha if alpha is None else alpha
+        _, _, out3 = self.monte_carlo_constraints(Z, t_risk)
+        return t_risk + float(out3[0]) / (self.M * alpha)
 
     # ---- IPOPT-callback style helpers (write into caller-owned arrays, :586-628) ---------
     def eval_g_into(self, x, out, row_offset):

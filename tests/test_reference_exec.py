@@ -172,3 +172,17 @@ def test_c_port_vs_reference_fixture(drone_seed0):
     assert np.allclose(ub, g["u"][row_s0:row_s0 + 60 * M], rtol=1e-11, atol=1e-13)
     assert np.allclose(sums[-6:] / M, g["l"][:6], rtol=1e-11, atol=1e-13)
     assert np.allclose(Z - 1e-3, g["Z"], rtol=1e-11, atol=1e-13)
+
+
+@pytest.mark.parametrize("M,method", [(50, 'baseline'), (8, 'baseline'), (1, 'saa'), (2, 'saa'), (3, 'saa'),
+                                      (1, 'baseline')])
+def test_library_relaxed_pattern_equals_the_reference(built_lib, M, method):
+    """The closed-form CSC pattern of libsaa_b200 (host code, no GPU) for the car's scp_iter 0
+    against what the reference's dense scan produces."""
+    from riskaversetrajopt_b200.pattern import csc_pattern
+    g = np.load(os.path.join(G, "ref_car_relaxed_edge.npz"))
+    for name, relaxed in (("iter0", True), ("iter1", False)):
+        k = f"{method}_M{M}_{name}"
+        n_rows, n_cols, indptr, indices = csc_pattern('car', method, 20, M, relaxed_pattern=relaxed)
+        assert (n_rows, n_cols) == tuple(g[k + "_shape"])
+        assert np.array_equal(indptr, g[k + "_indptr"]) and np.array_equal(indices, g[k + "_indices"])
