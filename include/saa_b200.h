@@ -285,6 +285,10 @@ int saa_hopper_g(saa_handle *h, const saa_hopper_point *pt, const double *y_dev,
  * (y_i, slack, t), 1 and M alpha (row 0), -1 (rows -y_i).
  * replaces: the slip-risk slice of jacrev(g) in eval_jac_g (hopper/hopper.py:569, :594-596). */
 int saa_hopper_jac(saa_handle *h, const saa_hopper_point *pt, void *jac_dev, void *stream);
+/* saa_hopper_g and saa_hopper_jac at the same point in ONE pass over the features (IPOPT asks for
+ * eval_g and eval_jac_g at the same iterate): the 600 sincos per sample are evaluated once.      */
+int saa_hopper_g_jac(saa_handle *h, const saa_hopper_point *pt, const double *y_dev, void *g_dev,
+                     void *jac_dev, void *stream);
 /* hess_dev[10 * n_c] (always double): per contact the lower triangle of the symmetric block of
  * hessian(lambda . g) on (x0, x2, x3, f_z)_t, as ten arrays of n_c values in the order (0,0) (1,0)
  * (1,1) (2,0) (2,1) (2,2) (3,0) (3,1) (3,2) (3,3); lambda_dev: the M n_c multipliers of the sample

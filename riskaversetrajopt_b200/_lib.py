@@ -90,6 +90,7 @@ _PROTOTYPES = {
     "saa_check_finite": (C.c_int, [_H, C.POINTER(C.c_int64), C.c_void_p]),
     "saa_hopper_g": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "saa_hopper_jac": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "saa_hopper_g_jac": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "saa_hopper_hess": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "saa_hopper_cvar_terms": (C.c_int, [_H, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
     "saa_linearize_means": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

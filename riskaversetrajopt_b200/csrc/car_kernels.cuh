@@ -264,10 +264,16 @@ __device__ void car_final_rows(const CarArgs<T, TO, S> &A, const CarEgo<T, S> &E
 template <typename T> struct CarChain { T rx, ry, wx, wy; };
 
 #ifndef SAA_CAR_WARPS
-#define SAA_CAR_WARPS 12   // warps per block (one block per SM; shared memory = WARPS x (geometry + staging))
+#define SAA_CAR_WARPS 16   // warps per block (one block per SM; shared memory = WARPS x (geometry + staging))
+#endif
+#ifndef SAA_CAR_COPY_RT
+#define SAA_CAR_COPY_RT 0  // 1: one run-time-parametrised copy loop for all columns; 0: unrolled per column
+#endif
+#ifndef SAA_CAR_GFORM
+#define SAA_CAR_GFORM 1    // 1: G rho = -om rho + (om n)(n . rho) reusing the entry's dot product; 0: dense 2x2 G
 #endif
 #ifndef SAA_CAR_CAP
-#define SAA_CAR_CAP 38     // staged values per sample and control in one chain pass (>= S-1); see CarPass
+#define SAA_CAR_CAP 23     // staged values per sample and control in one chain pass (>= S-1); see CarPass
 #endif
 
 // Kernel structure (round 2).  A warp owns a tile of 16 samples, lane = (sample, control c).
@@ -305,27 +311,82 @@ template <int S, int CAP> struct CarPass {
   }
   static constexpr int PER_C = kTileSamples * CAP;                  // staged block of one control
   static constexpr int UBROW = S | 1;
-  // pass A parks the noise [2][S][16] (in T) and stages the upper-bound rows 16 x UBROW (in TO)
-  __host__ __device__ static constexpr int stage_bytes(int szT, int szTO) {
-    const int a = 2 * S * kTileSamples * szT + kTileSamples * UBROW * szTO;
+  // pass A stages the upper-bound rows 16 x UBROW here, the chain passes their columns
+  __host__ __device__ static constexpr int stage_bytes(int szTO) {
+    const int a = kTileSamples * UBROW * szTO;
     const int b = 2 * PER_C * szTO;
     return ((a > b ? a : b) + 15) / 16 * 16;
   }
+  // Geometry rows of a warp: row 3k + q holds (n_x, n_y, om)[q] at state k for the 16 samples.
+  // Pass A parks the noise increment (k, c) in row DWBASE + 2k + c, i.e. in the rows of LATER
+  // states: step k writes rows 3k..3k+2 < DWBASE + 2k, the first noise row still unread.
+  static constexpr int GEO_ROWS = 3 * (S + 1);
+  static constexpr int DWBASE = GEO_ROWS - 2 * S;
 };
 
 template <typename T, typename TO, int S, int WARPS> struct CarSmem {
   using Ps = CarPass<S, SAA_CAR_CAP>;
-  static constexpr int STAGE_BYTES = Ps::stage_bytes((int)sizeof(T), (int)sizeof(TO));
+  static constexpr int STAGE_BYTES = Ps::stage_bytes((int)sizeof(TO));
   CarEgo<T, S> ego;
-  T geo[WARPS][3][S + 1][kTileSamples];                  // n_x, n_y, om per sample and state
+  T geo[WARPS][Ps::GEO_ROWS][kTileSamples];              // n_x, n_y, om per sample and state (CarPass)
   alignas(16) unsigned char stage[WARPS][STAGE_BYTES];
 };
 
+// Copy a column run (ns samples x L values, rows of stride L|1 in shared memory) to its
+// contiguous place in global memory with 16-byte streaming stores; the run starts 8-byte (4-byte)
+// aligned only, so up to VEC-1 head / tail elements go out as scalars.  L is a run-time value
+// (one instance of this code serves all columns: the fully unrolled per-column version was 200 KB
+// of SASS and stalled on instruction fetch); rows are found with a multiply-high by ceil(2^32/L).
+template <typename TO>
+__device__ __forceinline__ void car_copy_run(TO *__restrict__ dst, const TO *__restrict__ src, int L, int n,
+                                             int lane) {
+  constexpr int VEC = 16 / (int)sizeof(TO);
+  const int pad = (L & 1) ^ 1;                                   // row stride L|1
+  const unsigned magic = (unsigned)(0x100000000ull / (unsigned)L) + 1u;
+  auto at = [&](int e) -> TO { return src[e + (int)__umulhi((unsigned)e, magic) * pad]; };
+  const int head = min(n, (int)((VEC - (((uintptr_t)dst / sizeof(TO)) & (VEC - 1))) & (VEC - 1)));
+  const int nvec = (n - head) / VEC, tail = n - head - nvec * VEC;
+  if (lane < head) st_stream(dst + lane, at(lane));
+#pragma unroll 2
+  for (int v = lane; v < nvec; v += 32) {
+    const int e = head + v * VEC;
+    if constexpr (VEC == 2) {
+      double2 val;
+      val.x = (double)at(e); val.y = (double)at(e + 1);
+      __stcs(reinterpret_cast<double2 *>(dst + e), val);
+    } else {
+      float4 val;
+      val.x = (float)at(e); val.y = (float)at(e + 1); val.z = (float)at(e + 2); val.w = (float)at(e + 3);
+      __stcs(reinterpret_cast<float4 *>(dst + e), val);
+    }
+  }
+  if (lane < tail) st_stream(dst + head + nvec * VEC + lane, at(head + nvec * VEC + lane));
+}
+
+// columns j in [j0, j1) of both controls; position of the run in the CSC array: CarCol
+template <typename T, typename TO, int S>
+__device__ __forceinline__ void car_copy_cols(const CarArgs<T, TO, S> &A, const TO *stage, int j0, int j1,
+                                              i64 sbase, int ns, int lane) {
+  using Ps = CarPass<S, SAA_CAR_CAP>;
+  int off = 0;
+#pragma unroll 1
+  for (int j = j0; j < j1; ++j) {
+    const int L = S - 1 - j;
+    const i64 ca0 = 8 * j + 3, cb0 = (i64)2 * j * (S - 1) - (i64)j * (j - 1);
+    TO *d0 = A.Ax + (ca0 + A.M_out * cb0 + sbase * L);
+    TO *d1 = A.Ax + (ca0 + 4 + A.M_out * (cb0 + L) + sbase * L);
+    car_copy_run<TO>(d0, stage + off, L, ns * L, lane);
+    car_copy_run<TO>(d1, stage + Ps::PER_C + off, L, ns * L, lane);
+    off += kTileSamples * (L | 1);
+  }
+}
+
+// ---- compile-time unrolled variant of the copy-out (one instance per column; SAA_CAR_COPY_RT=0) ----
 // Copy a column run (ns samples x L values, rows of stride STRIDE in shared memory) to its
 // contiguous place in global memory with 16-byte streaming stores; the run starts 8-byte (4-byte)
 // aligned only, so up to VEC-1 head / tail elements go out as scalars.
 template <typename TO, int L, int STRIDE>
-__device__ __forceinline__ void car_copy_run(TO *__restrict__ dst, const TO *__restrict__ src, int n, int lane) {
+__device__ __forceinline__ void car_copy_run_t(TO *__restrict__ dst, const TO *__restrict__ src, int n, int lane) {
   constexpr int VEC = 16 / (int)sizeof(TO);
   auto at = [&](int e) -> TO { const int row = e / L; return src[e + row * (STRIDE - L)]; };
   const int head = min(n, (int)((VEC - (((uintptr_t)dst / sizeof(TO)) & (VEC - 1))) & (VEC - 1)));
@@ -348,36 +409,36 @@ __device__ __forceinline__ void car_copy_run(TO *__restrict__ dst, const TO *__r
 }
 
 template <typename T, typename TO, int S, int J0, int J, int J1>
-__device__ __forceinline__ void car_copy_cols(const CarArgs<T, TO, S> &A, const TO *stage, i64 sbase, int ns,
+__device__ __forceinline__ void car_copy_cols_t(const CarArgs<T, TO, S> &A, const TO *stage, i64 sbase, int ns,
                                               int lane) {
   if constexpr (J < J1) {
     using C = CarCol<S, J>;
     using Ps = CarPass<S, SAA_CAR_CAP>;
     i64 sb = sbase, mout = A.M_out;
     opaque(sb); opaque(mout);   // 2 IMADs per column instead of 2(S-1) live 64-bit bases
-    car_copy_run<TO, C::L, C::STRIDE>(A.Ax + (C::CA0 + mout * C::CB0 + sb * C::L), stage + Ps::pre(J0, J),
+    car_copy_run_t<TO, C::L, C::STRIDE>(A.Ax + (C::CA0 + mout * C::CB0 + sb * C::L), stage + Ps::pre(J0, J),
                                       ns * C::L, lane);
-    car_copy_run<TO, C::L, C::STRIDE>(A.Ax + (C::CA1 + mout * C::CB1 + sb * C::L),
+    car_copy_run_t<TO, C::L, C::STRIDE>(A.Ax + (C::CA1 + mout * C::CB1 + sb * C::L),
                                       stage + Ps::PER_C + Ps::pre(J0, J), ns * C::L, lane);
-    car_copy_cols<T, TO, S, J0, J + 1, J1>(A, stage, sbase, ns, lane);
+    car_copy_cols_t<T, TO, S, J0, J + 1, J1>(A, stage, sbase, ns, lane);
   }
 }
 
 // pass A: rollout, geometry -> shared memory, upper bounds, Z_i
 template <typename T, typename TO, int S>
 __device__ __forceinline__ void car_rollout_pass(const CarArgs<T, TO, S> &A, const CarEgo<T, S> &E,
-                                                 T (*geo)[S + 1][kTileSamples], unsigned char *stage_raw,
+                                                 T (*geo)[kTileSamples], unsigned char *stage_raw,
                                                  int c, int si, i64 s, T w_s, T w_r, T &zmax_out, bool &bad) {
   using Ps = CarPass<S, SAA_CAR_CAP>;
-  T (*dws)[S][kTileSamples] = reinterpret_cast<T (*)[S][kTileSamples]>(stage_raw);           // [2][S][16]
-  TO *ubrow = reinterpret_cast<TO *>(stage_raw + 2 * S * kTileSamples * sizeof(T)) + si * Ps::UBROW;
-  // this lane's half of the noise (c = 0: state 6, c = 1: state 7), all loads in flight at once
+  TO *ubrow = reinterpret_cast<TO *>(stage_raw) + si * Ps::UBROW;
+  // this lane's half of the noise (c = 0: state 6, c = 1: state 7), all loads in flight at once,
+  // parked in the geometry rows of later states (CarPass::DWBASE)
   {
     T tmp[S];
 #pragma unroll
     for (int k = 0; k < S; ++k) tmp[k] = __ldcs(A.dw + (i64)(2 * k + c) * A.Mpad + s);
 #pragma unroll
-    for (int k = 0; k < S; ++k) dws[c][k][si] = tmp[k];
+    for (int k = 0; k < S; ++k) geo[Ps::DWBASE + 2 * k + c][si] = tmp[k];
   }
   T qx = __ldcs(A.x0 + s), qy = __ldcs(A.x0 + A.Mpad + s);
   T wx = __ldcs(A.x0 + 2 * A.Mpad + s), wy = __ldcs(A.x0 + 3 * A.Mpad + s);
@@ -394,24 +455,23 @@ __device__ __forceinline__ void car_rollout_pass(const CarArgs<T, TO, S> &A, con
     bad |= !(n2 > T(0)) || !(n2 < T(INFINITY));
     const T nhx = dx * inv_n, nhy = dy * inv_n;
     const T om_n = dtwr * inv_n;
-    if (c == 0) { geo[0][k][si] = nhx; geo[2][k][si] = om_n; }
-    else geo[1][k][si] = nhy;
     if constexpr (k >= 1) {
       // upper bound -g_k + grad g_k . u (:278), grad g . u summed over both controls
       T gu = -fma(nhx, cu.rx, nhy * cu.ry);
-      gu += __shfl_xor_sync(0xffffffffu, gu, 16);
+      gu += __shfl_xor_sync(0xffffffffu, gu, 16);        // also: every lane has read the noise of step k-1
       const T g = A.d_min - n2 * inv_n;
       zmax = fmax(zmax, g);
       if (c == (k & 1)) ubrow[k - 1] = (TO)(gu - g);
     }
+    if (c == 0) { geo[3 * k][si] = nhx; geo[3 * k + 2][si] = om_n; }
+    else geo[3 * k + 1][si] = nhy;
     if constexpr (k < S) {
-      const T g11 = -om_n * fma(-nhx, nhx, T(1)), g12 = om_n * nhx * nhy,
-              g22 = -om_n * fma(-nhy, nhy, T(1));             // dt * dF/dp_ego
+      // dt dF/dp_ego = G_k = -om (I - n n^T)
       const T ttx = E.tt[c][k][0], tty = E.tt[c][k][1];
       const T uc = E.ucum[c][k];
-      const T sy = wsdt * cu.wy;
-      const T nwx = fma(g11, cu.rx, fma(g12, cu.ry, cu.wx - sy));
-      const T nwy = fma(g12, cu.rx, fma(g22, cu.ry, cu.wy - sy));
+      const T d = fma(nhx, cu.rx, nhy * cu.ry);
+      const T nwx = fma(om_n * nhx, d, fma(-om_n, cu.rx, fma(-wsdt, cu.wy, cu.wx)));
+      const T nwy = fma(om_n * nhy, d, fma(-om_n, cu.ry, fma(-wsdt, cu.wy, cu.wy)));
       cu.rx = fma(-dt, cu.wx, fma(uc, ttx, cu.rx));
       cu.ry = fma(-dt, cu.wy, fma(uc, tty, cu.ry));
       cu.wx = nwx; cu.wy = nwy;
@@ -419,8 +479,8 @@ __device__ __forceinline__ void car_rollout_pass(const CarArgs<T, TO, S> &A, con
       const T sp = w_s * (A.v_des - wy);
       const T fx = fma(-w_r, nhx, sp), fy = fma(-w_r, nhy, sp);
       const T nqx = fma(dt, wx, qx), nqy = fma(dt, wy, qy);
-      wx = wx + dt * fx + A.noise_c * dws[0][k][si];
-      wy = wy + dt * fy + A.noise_c * dws[1][k][si];
+      wx = wx + dt * fx + A.noise_c * geo[Ps::DWBASE + 2 * k][si];
+      wy = wy + dt * fy + A.noise_c * geo[Ps::DWBASE + 2 * k + 1][si];
       qx = nqx; qy = nqy;
     }
   });
@@ -431,7 +491,7 @@ __device__ __forceinline__ void car_rollout_pass(const CarArgs<T, TO, S> &A, con
 // geometry pass A left in shared memory.
 template <typename T, typename TO, int S, int J0, int J1>
 __device__ __forceinline__ void car_chain_pass(const CarArgs<T, TO, S> &A, const CarEgo<T, S> &E,
-                                               const T (*geo)[S + 1][kTileSamples], TO *stage, int c, int si,
+                                               const T (*geo)[kTileSamples], TO *stage, int c, int si,
                                                T wsdt) {
   using Ps = CarPass<S, SAA_CAR_CAP>;
   constexpr int NJ = J1 - J0;
@@ -445,19 +505,36 @@ __device__ __forceinline__ void car_chain_pass(const CarArgs<T, TO, S> &A, const
     constexpr int JE = (k - 1 < J1) ? (k - 1) : J1;          // exclusive end
     constexpr bool ALIVE = JE > J0;
     T nhx = T(0), nhy = T(0);
+    [[maybe_unused]] T dot[NJ > 0 ? NJ : 1];   // n_k . rho_k per chain: the (negated) entry AND what G_k rho_k needs
     if constexpr (ALIVE) {
-      nhx = geo[0][k][si]; nhy = geo[1][k][si];
+      nhx = geo[3 * k][si]; nhy = geo[3 * k + 1][si];
       // row k of the sample: d g_k / d u_{j,c} = -n_k . rho_k^{(j,c)}
       static_for<J0, JE>([&](auto jc) {
         constexpr int j = decltype(jc)::value;
-        cstage[Ps::pre(J0, j) + si * CarCol<S, j>::STRIDE + (k - j - 2)] =
-            (TO)(-fma(nhx, ch[j - J0].rx, nhy * ch[j - J0].ry));
+        dot[j - J0] = fma(nhx, ch[j - J0].rx, nhy * ch[j - J0].ry);
+        cstage[Ps::pre(J0, j) + si * CarCol<S, j>::STRIDE + (k - j - 2)] = (TO)(-dot[j - J0]);
       });
     }
     if constexpr (k < S) {
       const T ttx = E.tt[c][k][0], tty = E.tt[c][k][1];
       if constexpr (ALIVE) {
-        const T om_n = geo[2][k][si];
+#if SAA_CAR_GFORM
+        // dt dF/dp_ego = G_k = -om (I - n n^T):  G rho = -om rho + (om n) (n . rho)
+        const T om_n = geo[3 * k + 2][si];
+        const T onx = om_n * nhx, ony = om_n * nhy;
+        static_for<J0, JE>([&](auto jc) {
+          constexpr int j = decltype(jc)::value;
+          CarChain<T> &h = ch[j - J0];
+          const T d = dot[j - J0];
+          const T nwx = fma(onx, d, fma(-om_n, h.rx, fma(-wsdt, h.wy, h.wx)));
+          const T nwy = fma(ony, d, fma(-om_n, h.ry, fma(-wsdt, h.wy, h.wy)));
+          h.rx = fma(-dt, h.wx, h.rx + ttx);
+          h.ry = fma(-dt, h.wy, h.ry + tty);
+          h.wx = nwx; h.wy = nwy;
+        });
+      }
+#else
+        const T om_n = geo[3 * k + 2][si];
         const T g11 = -om_n * fma(-nhx, nhx, T(1)), g12 = om_n * nhx * nhy,
                 g22 = -om_n * fma(-nhy, nhy, T(1));           // dt * dF/dp_ego
         static_for<J0, JE>([&](auto jc) {
@@ -471,6 +548,7 @@ __device__ __forceinline__ void car_chain_pass(const CarArgs<T, TO, S> &A, const
           h.wx = nwx; h.wy = nwy;
         });
       }
+#endif
       // chain j = k-1 is born at this step: rho_{k+1} = T_c(k), w_{k+1} = 0
       if constexpr (k - 1 >= J0 && k - 1 < J1) {
         ch[k - 1 - J0].rx = ttx; ch[k - 1 - J0].ry = tty; ch[k - 1 - J0].wx = T(0); ch[k - 1 - J0].wy = T(0);
@@ -481,14 +559,18 @@ __device__ __forceinline__ void car_chain_pass(const CarArgs<T, TO, S> &A, const
 
 template <typename T, typename TO, int S, int P>
 __device__ __forceinline__ void car_passes(const CarArgs<T, TO, S> &A, const CarEgo<T, S> &E,
-                                           const T (*geo)[S + 1][kTileSamples], TO *stage, int c, int si,
+                                           const T (*geo)[kTileSamples], TO *stage, int c, int si,
                                            int lane, i64 s0, int ns, T wsdt) {
   using Ps = CarPass<S, SAA_CAR_CAP>;
   if constexpr (P < Ps::NPASS) {
     constexpr int J0 = Ps::bound(P), J1 = Ps::bound(P + 1);
     car_chain_pass<T, TO, S, J0, J1>(A, E, geo, stage, c, si, wsdt);
     __syncwarp();
-    car_copy_cols<T, TO, S, J0, J0, J1>(A, stage, s0 + A.first_out, ns, lane);
+#if SAA_CAR_COPY_RT
+    car_copy_cols<T, TO, S>(A, stage, J0, J1, s0 + A.first_out, ns, lane);
+#else
+    car_copy_cols_t<T, TO, S, J0, J0, J1>(A, stage, s0 + A.first_out, ns, lane);
+#endif
     __syncwarp();
     car_passes<T, TO, S, P + 1>(A, E, geo, stage, c, si, lane, s0, ns, wsdt);
   }
@@ -508,7 +590,7 @@ car_assemble_kernel(const __grid_constant__ CarArgs<T, TO, S> A) {
   if (blockIdx.x == 0 && A.sums != nullptr) car_final_rows<T, TO, S>(A, sm.ego, threadIdx.x, WARPS * 32);
   if (A.Ax == nullptr) return;              // relaxed iteration: only the final rows are needed
   const CarEgo<T, S> &E = sm.ego;
-  T (*geo)[S + 1][kTileSamples] = sm.geo[warp];
+  T (*geo)[kTileSamples] = sm.geo[warp];
   unsigned char *stage_raw = sm.stage[warp];
   bool bad = false;
 
@@ -527,9 +609,7 @@ car_assemble_kernel(const __grid_constant__ CarArgs<T, TO, S> A) {
     if (A.Z != nullptr && c == 0 && active) A.Z[s] = (TO)(zmax - A.ztol);
     __syncwarp();
     if (A.ub != nullptr)
-      car_copy_run<TO, S, Ps::UBROW>(A.ub + A.ub_off + s0 * S,
-                                     reinterpret_cast<const TO *>(stage_raw + 2 * S * kTileSamples * sizeof(T)),
-                                     ns * S, lane);
+      car_copy_run<TO>(A.ub + A.ub_off + s0 * S, reinterpret_cast<const TO *>(stage_raw), S, ns * S, lane);
     __syncwarp();
     car_passes<T, TO, S, 0>(A, E, geo, reinterpret_cast<TO *>(stage_raw), c, si, lane, s0, ns, w_s * A.dt);
   }

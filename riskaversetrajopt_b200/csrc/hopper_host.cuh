@@ -2,7 +2,7 @@
 namespace {
 
 #ifndef SAA_HOPPER_SMEM_KB
-#define SAA_HOPPER_SMEM_KB 24   // feature staging per block: 24 KB -> 9 blocks (36 warps) per SM
+#define SAA_HOPPER_SMEM_KB 36   // feature staging per block (48 B per feature): 6 blocks (24 warps) per SM
 #endif
 
 struct HopperOut {
@@ -31,7 +31,7 @@ int launch_hopper(saa_handle *h, const saa_hopper_point &pt, const HopperOut &o,
   const bool hess = o.lambda != nullptr, cvar = o.out3 != nullptr || o.Z != nullptr;
   // chunk of samples staged per block iteration: features (4 doubles each) within the budget, and a
   // multiple of the block size in (sample, contact) pairs when one exists
-  const size_t per_sample = 4 * sizeof(T) * (size_t)h->n_feat +
+  const size_t per_sample = sizeof(HopperFeat<T>) * (size_t)h->n_feat +
                             ((hess ? 2 : 0) + (cvar ? 1 : 0)) * sizeof(double) * (size_t)n_c;
   int cap = (int)std::max<size_t>(1, std::min<size_t>(64, ((size_t)SAA_HOPPER_SMEM_KB * 1024) / per_sample));
   int chunk = cap;
@@ -156,6 +156,22 @@ int saa_hopper_g(saa_handle *h, const saa_hopper_point *pt, const double *y, voi
   cudaStream_t st = (cudaStream_t)stream;
   const size_t es = h->precision == 64 ? 8 : 4;
   HopperOut o; o.y = saa ? y : nullptr;
+  o.g = saa ? (void *)((char *)g + (size_t)(1 + h->M_local) * es) : g;
+  if (int rc = hopper_dispatch(h, *pt, o, st)) return rc;
+  if (!saa) return SAA_OK;
+  return h->precision == 64 ? launch_hopper_head<double>(h, *pt, y, g, st) : launch_hopper_head<float>(h, *pt, y, g, st);
+}
+
+int saa_hopper_g_jac(saa_handle *h, const saa_hopper_point *pt, const double *y, void *g, void *jac,
+                     void *stream) {
+  if (int rc = hopper_check(h, pt)) return rc;
+  if (!g || !jac) return fail(h, SAA_ERR_ARG, "NULL argument");
+  const bool saa = h->method == SAA_METHOD_SAA;
+  if (saa && !y) return fail(h, SAA_ERR_ARG, "method saa needs the risk variables y_dev");
+  SAA_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t es = h->precision == 64 ? 8 : 4;
+  HopperOut o; o.y = saa ? y : nullptr; o.jac = jac;
   o.g = saa ? (void *)((char *)g + (size_t)(1 + h->M_local) * es) : g;
   if (int rc = hopper_dispatch(h, *pt, o, st)) return rc;
   if (!saa) return SAA_OK;

@@ -27,6 +27,10 @@ namespace saa {
 
 constexpr int kHopperMaxContacts = 32;
 constexpr int kHopperThreads = 128;
+#ifndef SAA_HOPPER_UNROLL
+#define SAA_HOPPER_UNROLL 4
+#endif
+constexpr int kHopperUnroll = SAA_HOPPER_UNROLL;   // features interleaved in the inner loop
 
 // T = arithmetic / feature type, TO = storage type of the outputs (double | float)
 template <typename T, typename TO> struct HopperArgs {
@@ -51,27 +55,79 @@ template <typename T, typename TO> struct HopperArgs {
   double *cvar;               // per-block [gridDim.x][3]: sum max(Z - t, 0), #{Z <= sat_tol}, max Z (optional)
 };
 
-// one staged feature: 32 bytes in FP64 (two 16-byte shared loads)
-template <typename T> struct __align__(4 * sizeof(T)) HopperFeat { T I, th, ta, nit; };   // nit = -I theta
+// One staged feature (48 bytes, three 16-byte shared loads; the fast path reads the first two):
+// th2 = theta 2/pi and ta2 = tau 2/pi give the argument in quarter turns, nit = -I theta.
+template <typename T> struct __align__(16) HopperFeat { T I, nit, th2, ta2, th, ta; };
+
+// sin / cos of (pi/2) y for y = th2 p + ta2 in QUARTER TURNS: n = rint(y) by the 1.5 2^52 shift,
+// f = y - n exactly (|f| <= 1/2), then sin(pi/2 f) = f P(f^2), cos(pi/2 f) = 1 + f^2 Q(f^2) with the
+// fdlibm minimax kernels rescaled by powers of pi/2 (|error| <= 1.2e-16 on |f| <= 1/2, checked with
+// mpmath), quadrant fix-up on the integer pipe.  19 FP64 instructions per feature instead of the 22
+// of sincos_core + the argument FMA: the three-step Cody-Waite reduction is replaced by an exact
+// subtraction.  The argument carries the rounding of th2 p + ta2, i.e. a few ulp(|x|) like
+// numpy's cos(theta p + tau) itself; callers switch to the library routine for |x| >= 1e5.
+struct HopperPoly { double s[7], c[7]; };
+__constant__ HopperPoly kHopperPoly = {
+    {1.5707963267948966192, -0.6459640975062449269, 0.079692626246063343923, -0.0046817541326259334138,
+     0.00016044115266738095834, -3.5986495702406919016e-6, 5.6347041138847509518e-8},
+    {-1.2337005501361698274, 0.25366950790104761936, -0.020863480763330759822, 0.00091926027439055337847,
+     -0.000025202037916917742371, 4.7106415058035018794e-7, -6.3247466788660698911e-9}};
+
+__device__ __forceinline__ void sincos_turn(double y, const HopperPoly &K, double *s, double *c) {
+  const double SHIFT = 6755399441055744.0;                    // 1.5 * 2^52
+  const double t = y + SHIFT;                                 // integer part of y in the low bits
+  const int n = __double2loint(t);
+  const double f = y - (t - SHIFT);
+  const double z = f * f;
+  double ps = fma(z, K.s[6], K.s[5]);
+  ps = fma(z, ps, K.s[4]);
+  ps = fma(z, ps, K.s[3]);
+  ps = fma(z, ps, K.s[2]);
+  ps = fma(z, ps, K.s[1]);
+  ps = fma(z, ps, K.s[0]);
+  const double sn = f * ps;
+  double pc = fma(z, K.c[6], K.c[5]);
+  pc = fma(z, pc, K.c[4]);
+  pc = fma(z, pc, K.c[3]);
+  pc = fma(z, pc, K.c[2]);
+  pc = fma(z, pc, K.c[1]);
+  pc = fma(z, pc, K.c[0]);
+  const double cs = fma(z, pc, 1.0);
+  // n mod 4: 0 (s, c)  1 (c, -s)  2 (-s, -c)  3 (-c, s)
+  const bool swap = n & 1;
+  double so = swap ? cs : sn, co = swap ? sn : cs;
+  so = __hiloint2double(__double2hiint(so) ^ ((n & 2) << 30), __double2loint(so));
+  co = __hiloint2double(__double2hiint(co) ^ (((n + 1) & 2) << 30), __double2loint(co));
+  *s = so; *c = co;
+}
 
 template <typename T, bool HESS, bool BIG>
-__device__ __forceinline__ void hopper_element(const HopperFeat<T> *row, int F, T p, T &m0, T &m1, T &m2) {
-#pragma unroll 2
+__device__ __forceinline__ void hopper_element(const HopperFeat<T> *row, int F, T p, const HopperPoly &K,
+                                               T &m0, T &m1, T &m2) {
+#pragma unroll kHopperUnroll
   for (int f = 0; f < F; ++f) {
-    const HopperFeat<T> ft = row[f];
-    const T x = fma(ft.th, p, ft.ta);
-    T sn, cs;
-    if (BIG) sincos_t(x, &sn, &cs);      // library routine (any argument)
-    else sincos_core(x, &sn, &cs);       // branch free
-    m0 = fma(ft.I, cs, m0);
-    m1 = fma(ft.nit, sn, m1);
-    if (HESS) m2 = fma(ft.nit * ft.th, cs, m2);
+    T sn, cs, I, nit, th;
+    if (BIG) {
+      const HopperFeat<T> ft = row[f];
+      sincos_t(fma(ft.th, p, ft.ta), &sn, &cs);      // library routine (any argument)
+      I = ft.I; nit = ft.nit; th = ft.th;
+    } else {
+      const double4 q = *reinterpret_cast<const double4 *>(&row[f]);     // I, nit, th2, ta2
+      sincos_turn(fma(q.z, p, q.w), K, &sn, &cs);    // branch free
+      I = q.x; nit = q.y; th = HESS ? row[f].th : T(0);
+    }
+    m0 = fma(I, cs, m0);
+    m1 = fma(nit, sn, m1);
+    if (HESS) m2 = fma(nit * th, cs, m2);
   }
 }
 
 // Shared memory: [features CH x F] [HESS: 2 x CH x n_c doubles] [CVAR: CH x n_c doubles]
+#ifndef SAA_HOPPER_MINBLOCKS
+#define SAA_HOPPER_MINBLOCKS 6    // <= 85 registers: 4 features in flight per thread, coefficients in (uniform) registers
+#endif
 template <typename T, typename TO, bool HESS, bool CVAR>
-__global__ void __launch_bounds__(kHopperThreads)
+__global__ void __launch_bounds__(kHopperThreads, SAA_HOPPER_MINBLOCKS)
 hopper_friction_kernel(const __grid_constant__ HopperArgs<T, TO> A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int F = A.F, n_c = A.n_c, CH = A.chunk;
@@ -87,6 +143,11 @@ hopper_friction_kernel(const __grid_constant__ HopperArgs<T, TO> A) {
     for (int e = threadIdx.x; e < 2 * CH * n_c; e += kHopperThreads) sw[e] = 0.0;
   }
   double acc_excess = 0.0, acc_sat = 0.0, acc_max = -INFINITY;
+  // polynomial coefficients pinned in registers: left in the constant bank they are re-loaded
+  // (LDC) inside the feature loop, in front of the FMAs that consume them
+  HopperPoly K = kHopperPoly;
+#pragma unroll
+  for (int q = 0; q < 7; ++q) { opaque(K.s[q]); opaque(K.c[q]); }
   T pmax = T(0);
   for (int c = 0; c < n_c; ++c) pmax = fmax(pmax, fabs(A.px[c]));
   const i64 N = A.M * n_c;
@@ -100,6 +161,7 @@ hopper_friction_kernel(const __grid_constant__ HopperArgs<T, TO> A) {
       for (int e = threadIdx.x; e < ns * F; e += kHopperThreads) {
         HopperFeat<T> ft;
         ft.I = __ldcs(gI + e); ft.th = __ldcs(gTh + e); ft.ta = __ldcs(gTa + e); ft.nit = -ft.I * ft.th;
+        ft.th2 = ft.th * T(0.63661977236758134308); ft.ta2 = ft.ta * T(0.63661977236758134308);
         sF[e] = ft;
         big |= sincos_big(fma(fabs(ft.th), pmax, fabs(ft.ta)));
       }
@@ -108,8 +170,8 @@ hopper_friction_kernel(const __grid_constant__ HopperArgs<T, TO> A) {
     for (int e = threadIdx.x; e < ns * n_c; e += kHopperThreads) {
       const int il = e / n_c, c = e - il * n_c;
       T m0 = T(0), m1 = T(0), m2 = T(0);
-      if (big) hopper_element<T, HESS, true>(sF + il * F, F, A.px[c], m0, m1, m2);
-      else hopper_element<T, HESS, false>(sF + il * F, F, A.px[c], m0, m1, m2);
+      if (big) hopper_element<T, HESS, true>(sF + il * F, F, A.px[c], K, m0, m1, m2);
+      else hopper_element<T, HESS, false>(sF + il * F, F, A.px[c], K, m0, m1, m2);
       const i64 g = i0 * n_c + e;
       const T mu = A.mu_nom + m0;
       const T cons = fma(-mu, A.fz[c], A.fx[c]);       // f_x - mu_i(p) f_z  (hopper.py:318-325)

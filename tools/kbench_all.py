@@ -71,4 +71,18 @@ if "hopper" in ONLY:
         print(f"hopper friction {prec} (g, jac): {t:.3f} ms for M={Mh}: {Mh*600/t/1e6:.1f} G sincos/s, {Mh*1520/t/1e6:.0f} GB/s algorithmic")
         t = timeit(lambda: hop(True))
         print(f"hopper friction {prec} (+ Hessian sums): {t:.3f} ms for M={Mh}: {Mh*600/t/1e6:.1f} G sincos/s")
+        Z = rs.uniform(-1, 1, hp.num_vars(Mh)) if prec == "fp64" else Z
+        import ctypes as C
+        pt = m._point(Z)
+        y = torch.as_tensor(Z[(hp.S + 1) * 8 + hp.S * 4:-2].copy()).to(dev)
+        gbuf = torch.empty(m.n_rows, dtype=m._jac_dev.dtype, device=dev)
+        def g_and_jac():
+            _lib.check(_lib.lib.saa_hopper_g(m._h, C.byref(pt), y.data_ptr(), gbuf.data_ptr(), m._stream()), m._h)
+            _lib.check(_lib.lib.saa_hopper_jac(m._h, C.byref(pt), m._jac_dev.data_ptr(), m._stream()), m._h)
+        t = timeit(g_and_jac)
+        es = 8 if prec == "fp64" else 4
+        print(f"hopper saa_hopper_g + saa_hopper_jac {prec}: {t:.3f} ms for M={Mh} (two launches, {2*Mh*600/t/1e6:.1f} G sincos/s; "
+              f"{Mh*(2*720+100*es)/t/1e6:.0f} GB/s: 720 B read per launch, {100*es} B written per sample)")
+        t = timeit(lambda: _lib.check(_lib.lib.saa_hopper_jac(m._h, C.byref(pt), m._jac_dev.data_ptr(), m._stream()), m._h))
+        print(f"hopper saa_hopper_jac {prec}: {t:.3f} ms ({Mh*600/t/1e6:.1f} G sincos/s)")
         del m
