@@ -12,16 +12,26 @@ the all-reduce of the 123 sample-mean sums).  Prints ONE JSON line.
 
   value   : M_total * S / t_step, inputs resident in HBM, device-timed (CUDA
             events on the launching stream, max over ranks).
-  e2e     : same metric through the host-facing call (host `us` in, pinned host
-            A.data u-block / u / l out, copies inside the timed region).
+  e2e     : same metric through the reference-facing plugin call
+            Model.get_constraints_coeffs(us, 2, copy=False): host `us` in, the
+            (A csc, l, u) the host QP solver consumes out, in pinned host memory; only
+            the iterate-dependent values cross PCIe (1140 M + 60 M + 123 for the drone).
+  e2e_tail: the tail-reduced subproblem through TailSubproblem.get_constraints_coeffs
+            (what a host solver can actually ingest at M = 10^6), N = 1.
   roofline: algorithmic bytes (10 144 B per sample, SURVEY 8d / DESIGN.md) /
             kernel time vs the measured HBM peak in MEASURED_PEAKS.json.
-  cpu_baseline: the oracle port on the host cores over a bounded sample.
+  problems: BASELINE configs 2 and 3 on the same GPU: car and hopper kernel times with
+            their HBM and FP64 rooflines (FP64 peak measured live: saa_measure_fp64_peak).
+  cpu_baseline: the oracle's C/OpenMP port on the host cores over a bounded sample.
+  multi_gpu_parity (N > 1): every delivery mode of dist.py against one GPU assembling
+            the same 4 096 samples (max relative error per mode).
 
---impl reference times the reference's own algorithm on the host CPU: Oracle-A
-(vmapped forward-mode autodiff + dense packing + SciPy CSR->CSC, i.e.
-drone/drone_risk.py:239-423 restated with torch.func because JAX is not in the
-image) on a bounded sample of the same workload.
+--impl reference times the reference's algorithm on the host CPU.  The reference itself
+(JAX) cannot run here or on the GPU box; its strongest faithful CPU stand-in is the
+oracle's C/OpenMP port (closed-form derivatives, values written straight into the CSC
+array, all host threads) -- that is the arm's value.  The literal algorithm (vmapped
+forward-mode autodiff + dense O(M^2) packing + SciPy CSR->CSC, oracle_a) is timed beside
+it on a few hundred samples as context ("dense_algorithm").
 """
 import argparse
 import json
@@ -168,44 +178,90 @@ def bench_us():
 
 # --------------------------------------------------------------------------- CPU legs
 def cpu_port_baseline(M_s=None, budget_s=12.0):
-    """Oracle port (analytic restatement) on the host cores over a bounded sample."""
+    """Oracle port (analytic restatement, C + OpenMP) on the host cores over a bounded sample."""
     from oracle import cpu_port
     return cpu_port.time_drone(bench_us(), budget_s=budget_s, M_s=M_s)
 
 
+def _time_numpy_oracle(make, call, M_s, unit_scale, what, budget_s=4.0):
+    o = make()
+    call(o)
+    reps, t_total = 0, 0.0
+    while t_total < budget_s and reps < 50:
+        t0 = time.perf_counter()
+        call(o)
+        t_total += time.perf_counter() - t0
+        reps += 1
+    dt_step = t_total / reps
+    return {"value": M_s * unit_scale / dt_step, "unit": UNIT, "cores": 1, "kind": "port",
+            "ms_per_step": dt_step * 1e3, "sample": f"{what} on {M_s} samples, {reps} repetitions (NumPy, one thread)"}
+
+
+def car_cpu_baseline(M_s=20000):
+    """Oracle-B (closed-form NumPy restatement of car/driving.py:261-373) on a bounded sample."""
+    from oracle.oracle_b import CarOracleB
+    from riskaversetrajopt_b200.car.driving import sample_uncertain_parameters
+    st = np.random.get_state(); np.random.seed(0)
+    s = sample_uncertain_parameters(M_s, 'saa'); np.random.set_state(st)
+    us = np.full((S, 2), 0.01) + 0.1 * np.random.RandomState(0).randn(S, 2)
+    return _time_numpy_oracle(lambda: CarOracleB(*s, 'saa', 0.05), lambda o: o.per_sample(us), M_s, S,
+                              "oracle_b.CarOracleB.per_sample (values + Jacobians of all samples, no CSC packing)")
+
+
+def hopper_cpu_baseline(M_s=20000):
+    from oracle.oracle_hopper import HopperOracleB
+    rs = np.random.RandomState(0)
+    f = (0.025 * np.sqrt(2 / 30) * rs.uniform(0, 1, (M_s, 30)), rs.uniform(0, np.pi, (M_s, 30)),
+         rs.uniform(0, 2 * np.pi, (M_s, 30)))
+    px = np.linspace(0, 0.2, 20)
+    return _time_numpy_oracle(lambda: HopperOracleB(M_s, 'saa', 0.1, *f), lambda o: o.friction(px), M_s, 20,
+                              "oracle_hopper.HopperOracleB.friction (mu, mu', mu'' at the 20 contact instants)")
+
+
 def run_reference_arm(args):
-    """The reference's own algorithm on the CPU (see module docstring)."""
+    """The reference's algorithm on the host CPU (see module docstring)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import torch
-    from oracle.oracle_a import DroneOracleA
-    from riskaversetrajopt_b200.drone import drone_params as dp
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    M_s = args.ref_samples
-    rs = np.random.RandomState(0)
-    masses = rs.uniform(dp.mass_nom - dp.mass_delta, dp.mass_nom + dp.mass_delta, M_s)
-    obs_Qs = np.zeros((M_s, 3, 3, 3))
-    for o in range(3):
-        for d in range(3):
-            obs_Qs[:, o, d, d] = 1. / (dp.obs_radii[o] + rs.uniform(-dp.obs_radii_deltas, dp.obs_radii_deltas, M_s))**2
-    DWs = np.sqrt(dp.dt) * rs.randn(M_s, S, 6)
-    model = DroneOracleA(S, DWs, masses, obs_Qs, 'saa', 0.1)
+    from oracle import cpu_port
+    cores_all = os.cpu_count() or 1
     us = bench_us()
-    for _ in range(args.warmup):
-        model.get_constraints_coeffs(us, 2)
+    M_s = args.ref_samples
+    masses, DWs, obs_Qs = cpu_port.synthetic_samples(M_s, S)
+    out = cpu_port.drone_assemble(us, masses, DWs, obs_Qs)
+    for _ in range(max(args.warmup, 1)):
+        cpu_port.drone_assemble(us, masses, DWs, obs_Qs, out=out)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        A, l, u = model.get_constraints_coeffs(us, 2)
+        cpu_port.drone_assemble(us, masses, DWs, obs_Qs, out=out)
     dt_step = (time.perf_counter() - t0) / args.steps
     value = M_s * S / dt_step
-    sample = (f"Oracle-A (torch.func vmap(jacfwd) + dense packing + SciPy CSR->CSC = the reference's "
-              f"algorithm, drone/drone_risk.py:239-423) on {M_s} of the 10^6 samples per step; "
-              f"dense matrix is O(M^2) so the reference cannot run the full workload")
+    cores = int(cpu_port._lib().saa_oracle_threads())
+    dense = None
+    if not args.no_dense:
+        try:
+            import torch
+            from oracle.oracle_a import DroneOracleA
+            torch.set_num_threads(cores_all)
+            Md = args.dense_samples
+            model = DroneOracleA(S, DWs[:Md], masses[:Md], obs_Qs[:Md], 'saa', 0.1)
+            model.get_constraints_coeffs(us, 2)
+            t0 = time.perf_counter()
+            for _ in range(2):
+                model.get_constraints_coeffs(us, 2)
+            td = (time.perf_counter() - t0) / 2
+            dense = {"value": Md * S / td, "unit": UNIT, "samples": Md, "ms_per_step": td * 1e3,
+                     "what": "oracle_a: the reference's literal algorithm (vmap(jacfwd) + dense O(M^2) packing + "
+                             "SciPy CSR->CSC, drone/drone_risk.py:239-423) with torch.func standing in for JAX; "
+                             "cannot reach the 10^6-sample workload (49 GB dense matrix at M = 10^4)"}
+        except Exception as exc:
+            dense = {"error": repr(exc)[:200]}
+    sample = (f"oracle/saa_oracle.c (closed-form restatement of drone/drone_risk.py:239-374 writing the CSC values "
+              f"directly into host memory; C + OpenMP, {cores} threads) on {M_s} of the 10^6 samples per step, "
+              f"output buffers reused")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 1),
         "ms_per_step": dt_step * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "drone SAA linearize+assemble, S=20, n_obs=3 (BASELINE config 4)",
@@ -213,17 +269,37 @@ def run_reference_arm(args):
                    "method": "saa"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "dense_algorithm": dense,
         "gpu_launches": 0,
     }))
 
 
 # --------------------------------------------------------------------------- our arm
+def _events(n):
+    import torch
+    return [torch.cuda.Event(enable_timing=True) for _ in range(n)]
+
+
+def _device_time(fn, stream, n=10, warm=3):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(n):
+        a, b = _events(2)
+        a.record(stream); fn(); b.record(stream)
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return float(np.median(ts))
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from riskaversetrajopt_b200 import _lib
-    from riskaversetrajopt_b200.device_path import DevicePath
+    from riskaversetrajopt_b200 import _lib, dist as sd
     from riskaversetrajopt_b200.drone import drone_params as dp
+    from riskaversetrajopt_b200.drone.drone_risk import Model
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -239,26 +315,27 @@ def run_ours(args):
     M = args.samples_per_gpu
     M_global = M * world
     DWs, masses, obs_Qs = synthetic_drone_samples(M, seed=rank, device=device)
-    path = DevicePath(_lib.SAA_DRONE, 'saa', S, 0.1, M, M_global=M_global, sample_offset=rank * M,
-                      device=local_rank)
-    path.set_params_drone(dp, dp.OSQP_TOL)
-    path.set_samples_drone(masses, DWs, obs_Qs)
-    # each rank keeps its own row block (compact matrix of its M samples) in its HBM
-    path.set_output_geometry(M, 0)
+    # the reference-facing object: Model of drone/drone_risk.py; each rank keeps its own row block
+    # (compact matrix of its M samples) in its HBM
+    model = Model(S, DWs, masses, obs_Qs, 'saa', 0.1, device=local_rank,
+                  shard=(M_global, rank * M) if world > 1 else None)
+    path = model.path
     torch.cuda.synchronize()
     del DWs, masses, obs_Qs
+    model.DWs = model.masses = model.obs_Qs = None
     path._keep = []
     torch.cuda.empty_cache()
     us = bench_us()
     scp_iter = 2
     stream = torch.cuda.current_stream(device)
+    overlap = sd.OverlappedMeans(path) if world > 1 else None
 
     def step():
         if world == 1:
             return path.assemble(us, scp_iter, finalize=True)
+        overlap.launch(us)                               # mean kernels + NCCL all-reduce, side stream
         b = path.assemble(us, scp_iter, finalize=False, write_shared=True)
-        dist.all_reduce(path.mean_sums)                  # NCCL, 123 doubles
-        path.finalize_means(b)
+        overlap.finalize(b, scp_iter)
         return b
 
     def barrier():
@@ -273,7 +350,7 @@ def run_ours(args):
         step()
     barrier()
     # ---- timed region: K steps, device events on the launching stream -------------
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ev = _events(args.steps + 1)
     barrier()
     mark_lo = sampler.mark()
     ev[0].record(stream)
@@ -291,8 +368,7 @@ def run_ours(args):
     value = M_global * S / (ms_per_step * 1e-3)
 
     # ---- kernel-only duration for the roofline (same stream, own events) ------------
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-           for _ in range(args.steps)]
+    kev = [tuple(_events(2)) for _ in range(args.steps)]
     torch.cuda.synchronize()
     for a, b_ in kev:
         a.record(stream)
@@ -302,60 +378,78 @@ def run_ours(args):
     kernel_ms = float(np.mean([a.elapsed_time(b_) for a, b_ in kev]))
     clocks = sampler.stop(mark_lo, mark_hi) if rank == 0 else None
 
-    # ---- e2e through the host-facing call: host us in, pinned host values out ------
+    # ---- e2e through the plugin call: host us in, (A csc, l, u) in pinned host memory out ------
     e2e = None
     try:
-        n_rows, n_cols, nnz = path.pattern_sizes()
-        n_var = 1140 * M + 177                           # u-column block of A.data (contiguous)
-        b = path.buffers()
-        hAx = torch.empty(n_var, dtype=torch.float64, pin_memory=True)
-        hu = torch.empty(n_rows, dtype=torch.float64, pin_memory=True)
-        hl = torch.empty(6, dtype=torch.float64, pin_memory=True)
-
         def e2e_step():
-            step()
-            hAx.copy_(b['Ax'][:n_var], non_blocking=True)
-            hu.copy_(b['u'], non_blocking=True)
-            hl.copy_(b['l'][:6], non_blocking=True)
-            stream.synchronize()
+            if world == 1:
+                return model.get_constraints_coeffs(us, scp_iter, copy=False)     # THE drop-in boundary
+            # sharded: the expectation rows need the all-reduced sums, then the same host delivery
+            overlap.launch(us)
+            b = path.assemble(us, scp_iter, finalize=False, write_shared=True)
+            overlap.finalize(b, scp_iter)
+            return path.csc(us, scp_iter, copy=False, assembled=b)
 
+        A, l, u = e2e_step()                             # first call: pinned allocation + full copy
         e2e_step()
         barrier()
         n_e2e = max(2, min(args.steps, 5))
         t0 = time.perf_counter()
         for _ in range(n_e2e):
-            e2e_step()
+            A, l, u = e2e_step()
         barrier()
         te = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device=device)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        assert A.shape == (68 + 61 * M, 62 + M) and A.data.size == 1263 * M + 180
         e2e = {"value": M_global * S / float(te.item()), "unit": UNIT,
-               "h2d_bytes_per_step": int(us.nbytes),
-               "d2h_bytes_per_step": int((n_var + n_rows + 6) * 8),
+               "h2d_bytes_per_step": int(us.nbytes), "d2h_bytes_per_step": int(path.d2h_bytes_per_call(scp_iter)),
                "ms_per_step": float(te.item()) * 1e3, "steps": n_e2e,
-               "what": "host us (480 B, kernel argument) -> pinned host A.data[u columns], u, l[:6]; "
-                       "static y/slack/t columns and the CSC pattern stay on the host from setup"}
-        del hAx, hu, hl
+               "call": "Model.get_constraints_coeffs(us, 2, copy=False) -> (A: scipy csc_matrix, l, u)"
+                       if world == 1 else "per rank: assemble + all-reduced means, then DevicePath.csc(..., copy=False) "
+                                          "(the delivery Model.get_constraints_coeffs makes) of the rank's row block",
+               "what": "host us (480 B, kernel argument) -> the full (A, l, u) of the drop-in boundary in pinned host "
+                       "memory; per call only the iterate-dependent values cross PCIe (u-column block of A.data, "
+                       "sample-row upper bounds, expectation-row bounds), the constant y/slack/t columns and the CSC "
+                       "pattern were transferred once"}
+        del A, l, u
+        path._pinned.clear(); path._csc_cache.clear(); path._host_state.clear()
     except Exception as exc:  # e.g. not enough pinned host memory
-        e2e = {"value": None, "unit": UNIT, "error": repr(exc)[:200]}
+        e2e = {"value": None, "unit": UNIT, "error": repr(exc)[:300]}
 
-    # ---- tail-reduced subproblem, context beside the headline: what the host
-    # QP solver needs when it is fed the K = 1.25 alpha M samples with the largest Z_i only
+    # ---- tail-reduced subproblem: what a host QP solver can ingest at M = 10^6
     tail = None
     if world == 1 and not args.no_tail:
         try:
-            tail = measure_tail(path, us, scp_iter, stream, device)
+            tail = measure_tail(model, us, scp_iter, stream, device)
         except Exception as exc:
             tail = {"error": repr(exc)[:200]}
 
-    # ---- BASELINE target configuration at N > 1: M = 10^6 samples IN TOTAL, row blocks
-    # delivered to rank 0 (fused peer-store gather over NVLink), reported beside the weak-scaling line
-    target = None
-    if world > 1 and not args.no_gather:
+    # ---- BASELINE configs 2 and 3 on the same GPU -----------------------------------------------
+    problems = None
+    if world == 1 and not args.no_problems:
+        del model, path
+        torch.cuda.empty_cache()
         try:
-            target = measure_target_config(args, rank, world, local_rank, device)
+            problems = measure_problems(args, device, stream)
         except Exception as exc:
-            target = {"error": repr(exc)[:300]}
+            problems = {"error": repr(exc)[:300]}
+
+    # ---- N > 1: delivery modes at M = 10^6 in total, and their parity against one GPU ------------
+    target = parity = None
+    if world > 1:
+        del model, path, overlap
+        torch.cuda.empty_cache()
+        if not args.no_parity:
+            try:
+                parity = measure_parity(rank, world, local_rank, device)
+            except Exception as exc:
+                parity = {"error": repr(exc)[:300]}
+        if not args.no_gather:
+            try:
+                target = measure_target_config(args, rank, world, local_rank, device)
+            except Exception as exc:
+                target = {"error": repr(exc)[:300]}
 
     if rank != 0:
         if world > 1:
@@ -369,7 +463,9 @@ def run_ours(args):
             cpu = cpu_port_baseline()
         except Exception as exc:
             cpu = {"value": None, "unit": UNIT, "error": repr(exc)[:200]}
-    launches_per_step = 4       # drone_assemble + drone_axis_mean + reduce_partials + scatter_means
+    # drone_assemble + drone_axis_mean + reduce_partials + scatter_means; N > 1: + 3 axis-mean kernels and their
+    # reduce on the side stream (the NCCL all-reduce kernel is not ours)
+    launches_per_step = 4 if world == 1 else 8
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -378,10 +474,11 @@ def run_ours(args):
                    "samples_per_gpu": M, "samples_total": M_global, "alpha": 0.1, "scp_iter": scp_iter,
                    "method": "saa", "l2": "per-step output 9.6 GB/GPU >> 126 MB L2 (no flush needed)",
                    "row_blocks": "sharded (each rank keeps its block in HBM)" if world > 1 else "single GPU",
-                   "collective": "all_reduce(123 f64) per step" if world > 1 else "none"},
+                   "collective": "all_reduce(123 f64) per step on a side stream, overlapped with the assemble kernel "
+                                 "(1 SM reserved for it)" if world > 1 else "none"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": _traffic(), "peak_source": peak_src,
-                     "kernel": "drone_assemble_kernel<double,20,6>", "kernel_ms": kernel_ms,
+                     "kernel": "drone_assemble_kernel<double,double,20,6,FULL>", "kernel_ms": kernel_ms,
                      "bytes_per_launch": M * BYTES_PER_SAMPLE,
                      "note": "event pair spans drone_assemble_kernel (97 % of it) plus drone_axis_mean_kernel "
                              "(z-axis mean rows, reads 168 of the 536 input bytes per sample) and the ~3 us "
@@ -392,43 +489,154 @@ def run_ours(args):
         "clocks": clocks,
         "per_step_ms": [round(x, 4) for x in per_step],
     }
+    if tail is not None:
+        out["e2e_tail"] = tail
+    if problems is not None:
+        out["problems"] = problems
+    if parity is not None:
+        out["multi_gpu_parity"] = parity
     if target is not None:
         out["target_config"] = target
-    if tail is not None:
-        out["tail_subproblem"] = tail
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
 
-def measure_tail(path, us, scp_iter, stream, device):
+def measure_tail(model, us, scp_iter, stream, device):
     """Per-iteration cost of the tail-reduced subproblem on one GPU: means + Z_i over all M samples,
     device selection of the K largest, gather, linearize+assemble of K samples; device-timed, and
-    end to end with the reduced (A.data, l, u) copied to pinned host memory."""
+    end to end through ``TailSubproblem.get_constraints_coeffs`` (reduced (A csc, l, u, idx) in pinned
+    host memory)."""
     import torch
-    from riskaversetrajopt_b200.tail import TailSubproblem
-    t = TailSubproblem(path, margin=0.25)
-    for _ in range(3):
-        t.assemble(us, scp_iter)
-    torch.cuda.synchronize()
-    n = 10
-    a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record(stream)
-    for _ in range(n):
-        t.assemble(us, scp_iter)
-    b_.record(stream)
-    torch.cuda.synchronize()
-    dev_ms = a.elapsed_time(b_) / n
+    t = model.tail_subproblem(margin=0.25)
+    M = model.path.M_local
+    dev_ms = _device_time(lambda: t.assemble(us, scp_iter), stream, n=10, warm=3)
+    t.get_constraints_coeffs(us, scp_iter, copy=False)
     t.get_constraints_coeffs(us, scp_iter, copy=False)
     t0 = time.perf_counter()
     for _ in range(5):
         A, l, u, idx = t.get_constraints_coeffs(us, scp_iter, copy=False)
-    e2e_ms = (time.perf_counter() - t0) / 5 * 1e3
-    return {"K": t.K, "M": path.M_local, "device_ms": dev_ms, "e2e_ms": e2e_ms,
-            "d2h_bytes_per_step": int(A.data.nbytes + l.nbytes + u.nbytes + idx.nbytes),
-            "note": "context, not the headline metric: QP restricted to the K samples with the largest "
-                    "max-constraint value at the iterate (exact when the samples left out stay inactive); "
-                    "e2e = host us -> (A.data, l, u, idx) of the reduced matrix in pinned host memory"}
+    e2e_s = (time.perf_counter() - t0) / 5
+    return {"value": M * S / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3, "device_ms": dev_ms,
+            "K": t.K, "M": M, "h2d_bytes_per_step": int(us.nbytes),
+            "d2h_bytes_per_step": int(t.d2h_bytes_per_call(scp_iter)),
+            "call": "TailSubproblem.get_constraints_coeffs(us, 2, copy=False) -> (A csc, l, u, idx)",
+            "note": "all M samples are rolled out and ranked on the device every step; the QP handed to the host "
+                    "solver is restricted to the K = 1.25 alpha M samples with the largest max-constraint value at the "
+                    "iterate (exact when the samples left out stay inactive: TailSubproblem.left_out_margin)"}
+
+
+def measure_problems(args, device, stream):
+    """BASELINE configs 2 (car) and 3 (hopper) at M = 10^6 synthetic samples on this GPU: device time
+    of the hot kernel, HBM and FP64 rooflines, CPU baseline of the oracle's closed forms."""
+    import ctypes as C
+    import torch
+    from riskaversetrajopt_b200 import _lib
+    from riskaversetrajopt_b200.device_path import DevicePath
+    from riskaversetrajopt_b200.car import driving_params as cp
+    from riskaversetrajopt_b200.car.driving import BETA
+    from riskaversetrajopt_b200.hopper import hopper as hp
+    hbm, hbm_src = _peaks()
+    fma = C.c_double()
+    _lib.check(_lib.lib.saa_measure_fp64_peak(device.index, C.byref(fma)))
+    fp64_peak = fma.value                                # FMA / s
+    M = args.samples_per_gpu
+    out = {"fp64_peak": {"fma_per_s": fp64_peak, "tflops": 2 * fp64_peak / 1e12,
+                         "source": "measured in this run: saa_measure_fp64_peak (8 dependent-FMA chains per thread, "
+                                   "32 warps/SM, best of 5; tools/fp64_peak.cu)"}}
+    # ---- car (car/driving.py): 3 576 algorithmic bytes per sample; FP64: 380 chain steps x 12 + rollout 21 x 45
+    g = torch.Generator(device=device); g.manual_seed(0)
+    f64 = dict(generator=g, device=device, dtype=torch.float64)
+    x0 = torch.as_tensor(np.asarray(cp.state_init, dtype=np.float64), device=device).repeat(M, 1)
+    x0[:, 4:] += torch.randn((M, 4), **f64) * torch.tensor([0.1, 0.1, 1e-4, 1e-4], device=device, dtype=torch.float64)
+    ws = 0.025 + 0.15 * torch.rand(M, **f64)
+    wr = 0.005 + 0.09 * torch.rand(M, **f64)
+    DW = float(np.sqrt(cp.dt)) * torch.randn((M, S, 8), **f64)
+    p = DevicePath(_lib.SAA_CAR, 'saa', S, 0.05, M, device=device.index)
+    p.set_params_car(cp, BETA, cp.OSQP_TOL); p.set_samples_car(x0, ws, wr, DW)
+    torch.cuda.synchronize(); p._keep = []
+    del x0, ws, wr, DW
+    usc = np.full((S, 2), 0.01) + 0.1 * np.random.RandomState(0).randn(S, 2)
+    t_car = _device_time(lambda: p.assemble(usc, 2, finalize=False), stream)
+    car_bytes, car_fma = 3576, 380 * 12 + 21 * 45
+    out["car"] = {
+        "workload": "car/driving.py SAA linearize+assemble, S=20, M=%d synthetic samples, scp_iter 2 (BASELINE config 2)" % M,
+        "kernel": "car_assemble_kernel<double,double,20,16>", "kernel_ms": t_car,
+        "value": M * S / (t_car * 1e-3), "unit": UNIT,
+        "roofline": {"bound": "hbm", "achieved": M * car_bytes / (t_car * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                     "frac": M * car_bytes / (t_car * 1e-3) / 1e9 / hbm, "bytes_per_sample": car_bytes, "peak_source": hbm_src},
+        "roofline_fp64": {"bound": "fp64", "achieved": M * car_fma / (t_car * 1e-3) / 1e12, "peak": fp64_peak / 1e12,
+                          "unit": "TFMA/s", "frac": M * car_fma / (t_car * 1e-3) / fp64_peak,
+                          "fma_per_sample": car_fma,
+                          "note": "algorithmic FP64 instructions per sample: 380 chain steps x 12 + one rollout of 21 "
+                                  "states x 45 (the kernel runs the rollout in both lanes of a sample)"},
+        "nonfinite_samples": p.check_finite(raise_error=False),
+    }
+    del p; torch.cuda.empty_cache()
+    # ---- hopper (hopper/hopper.py): one g + jac evaluation = 600 sincos + 1 520 B per sample
+    Mh = M
+    gen = torch.Generator(device=device); gen.manual_seed(1)
+    u = lambda *sh: torch.rand(*sh, generator=gen, device=device, dtype=torch.float64)
+    feats = (0.025 * float(np.sqrt(2 / 30)) * u(Mh, 30), float(np.pi) * u(Mh, 30), 2 * float(np.pi) * u(Mh, 30))
+    m = hp.Model(Mh, 'saa', 0.1, tuple(f.cpu().numpy() for f in feats))
+    del feats
+    rs = np.random.RandomState(0)
+    Z = rs.uniform(-1, 1, hp.num_vars(Mh))
+    pt = m._point(Z)
+    y = torch.as_tensor(Z[(hp.S + 1) * 8 + hp.S * 4:-2].copy()).to(device)
+    gbuf = torch.empty(m.n_rows, dtype=torch.float64, device=device)
+    def g_jac():
+        _lib.check(_lib.lib.saa_hopper_g_jac(m._h, C.byref(pt), y.data_ptr(), gbuf.data_ptr(), m._jac_dev.data_ptr(),
+                                             m._stream()), m._h)
+    t_hop = _device_time(g_jac, stream)
+    hop_bytes, hop_fma = 1520, 600 * 21
+    out["hopper"] = {
+        "workload": "hopper/hopper.py slip-risk block, one g + jac evaluation (saa_hopper_g_jac): 20 contact instants x 30 "
+                    "features, M=%d synthetic samples (BASELINE config 3)" % Mh,
+        "kernel": "hopper_friction_kernel<double,double,false,false>", "kernel_ms": t_hop,
+        "value": Mh * 20 / (t_hop * 1e-3), "unit": "samples*contacts/s",
+        "sincos_per_s": Mh * 600 / (t_hop * 1e-3),
+        "bytes_written_per_sample": 800,
+        "roofline": {"bound": "fp64", "achieved": Mh * hop_fma / (t_hop * 1e-3) / 1e12, "peak": fp64_peak / 1e12,
+                     "unit": "TFMA/s", "frac": Mh * hop_fma / (t_hop * 1e-3) / fp64_peak, "fma_per_sample": hop_fma,
+                     "note": "21 FP64 instructions per feature evaluation (19 for the sincos + 2 accumulations), 600 per sample"},
+        "roofline_hbm": {"bound": "hbm", "achieved": Mh * hop_bytes / (t_hop * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                         "frac": Mh * hop_bytes / (t_hop * 1e-3) / 1e9 / hbm, "bytes_per_sample": hop_bytes},
+    }
+    del m; torch.cuda.empty_cache()
+    if not args.no_cpu_baseline:
+        for name, fn in (("car", car_cpu_baseline), ("hopper", hopper_cpu_baseline)):
+            try:
+                out[name]["cpu_baseline"] = fn()
+            except Exception as exc:
+                out[name]["cpu_baseline"] = {"error": repr(exc)[:200]}
+    return out
+
+
+def _shard_maker(device, local_rank, M_total, seed):
+    """make_path(first, count, M_global) on identical synthetic samples on every rank."""
+    from riskaversetrajopt_b200 import _lib
+    from riskaversetrajopt_b200.device_path import DevicePath
+    from riskaversetrajopt_b200.drone import drone_params as dp
+    DWs, masses, obs_Qs = synthetic_drone_samples(M_total, seed=seed, device=device)
+
+    def make(first, cnt, M_global):
+        p = DevicePath(_lib.SAA_DRONE, 'saa', S, 0.1, cnt, M_global=M_global, sample_offset=first, device=local_rank)
+        p.set_params_drone(dp, dp.OSQP_TOL)
+        p.set_samples_drone(masses[first:first + cnt], DWs[first:first + cnt], obs_Qs[first:first + cnt])
+        return p
+    return make, (lambda q: q.set_params_drone(dp, dp.OSQP_TOL))
+
+
+def measure_parity(rank, world, local_rank, device, M=4096):
+    """GPUTEST runs on one GPU: verify the multi-GPU gathers here, where the driver's scaling run can
+    see it.  Every delivery mode against ONE GPU assembling the same samples."""
+    from riskaversetrajopt_b200 import dist as sd
+    make, setp = _shard_maker(device, local_rank, M, seed=4242)
+    res = sd.parity_self_check(make, setp, M, bench_us(), 2)
+    res["samples"] = M
+    res["metric"] = "max relative error vs a single-GPU assemble of the same samples (Ax u-block, l, u)"
+    return res
 
 
 def measure_target_config(args, rank, world, local_rank, device):
@@ -517,7 +725,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--samples-per-gpu", type=int, default=1_000_000)
-    ap.add_argument("--ref-samples", type=int, default=400)
+    ap.add_argument("--ref-samples", type=int, default=100_000)
+    ap.add_argument("--dense-samples", type=int, default=300)
+    ap.add_argument("--no-dense", action="store_true")
+    ap.add_argument("--no-problems", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gather", action="store_true")
     ap.add_argument("--no-tail", action="store_true")

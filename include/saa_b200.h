@@ -235,6 +235,17 @@ int saa_rollout(saa_handle *h, const double *us_host, void *Xs_dev, void *stream
 int saa_cvar_terms(saa_handle *h, const double *us_host, double t_risk,
                    double sat_tol, void *Z_dev, double *out3_dev, void *stream);
 
+/* The assemble kernels are persistent (one grid fills every SM and its register file), so a
+ * kernel launched on another stream -- e.g. the NCCL all-reduce of the mean sums -- cannot start
+ * before they finish.  Leaving `n_sms` SMs out of the persistent grids lets it run concurrently
+ * (multi-GPU steps reserve 1 of 148: 0.7 % of the kernel for ~75 us of exposed collective).   */
+int saa_reserve_sms(saa_handle *h, int n_sms);
+
+/* Measured FP64 FMA throughput (FMA / s) of `device`: 8 independent dependent-FMA chains per thread,
+ * 32 warps per SM, best of 5 launches.  The denominator of the FP64 rooflines bench.py reports for
+ * the car and hopper kernels (no reference counterpart; synchronous, takes a few ms).            */
+int saa_measure_fp64_peak(int device, double *fma_per_s);
+
 /*
  * Non-finite guard.  The car divides by |p_ego - p_ped| (car/driving.py:154); the reference
  * silently propagates NaN when the two coincide.  Every assemble / rollout launch counts the

@@ -44,8 +44,10 @@ struct saa_handle {
   int n_feat = 0; double mu_nom = 0.0;
   // scratch
   int n_sms = kSMs;
+  int reserve_sms = 0;         // SMs the persistent assemble grids leave free (saa_reserve_sms)
   double *d_partials = nullptr; i64 partials_len = 0;
   double *d_sums = nullptr;
+  double *d_means_scratch = nullptr; i64 means_scratch_len = 0;   // saa_linearize_means (may run on a side stream)
   i64 *d_fin_off = nullptr;          // [0..255]: normal pattern, [256..511]: car relaxed pattern
   void *d_relax_scratch = nullptr; i64 relax_scratch_bytes = 0;   // car scp_iter 0: sample 0 alone
   unsigned long long *d_nonfinite = nullptr;                      // samples with a non-finite rollout (saa_check_finite)
@@ -260,7 +262,7 @@ void fill_drone_common(const saa_handle *h, const double *us, T *us_out, T &dt, 
 
 int grid_for(const saa_handle *h, i64 ntiles, int warps, int blocks_per_sm) {
   const i64 want = (ntiles + warps - 1) / warps;
-  return (int)std::max<i64>(1, std::min<i64>(want, (i64)h->n_sms * blocks_per_sm));
+  return (int)std::max<i64>(1, std::min<i64>(want, (i64)std::max(1, h->n_sms - h->reserve_sms) * blocks_per_sm));
 }
 
 // same formula as DroneChain<S,J>::CA/CB (drone_kernels.cuh)
@@ -461,7 +463,7 @@ int saa_destroy(saa_handle *h) {
   cudaSetDevice(h->device);
   cudaFree(h->d_a); cudaFree(h->d_b); cudaFree(h->d_c); cudaFree(h->d_d);
   cudaFree(h->d_partials); cudaFree(h->d_sums); cudaFree(h->d_fin_off); cudaFree(h->d_relax_scratch);
-  cudaFree(h->d_nonfinite); cudaFree(h->d_hopper_geo);
+  cudaFree(h->d_nonfinite); cudaFree(h->d_hopper_geo); cudaFree(h->d_means_scratch);
   delete h;
   return SAA_OK;
 }
@@ -730,6 +732,59 @@ int saa_rollout(saa_handle *h, const double *us, void *Xs, void *stream) {
                               : launch_drone_rollout<float>(h, us, Xs, nullptr, 0, 0, 0, nullptr, st);
   return h->precision == 64 ? launch_car_rollout<double>(h, us, Xs, nullptr, 0, 0, 0, nullptr, st)
                             : launch_car_rollout<float>(h, us, Xs, nullptr, 0, 0, 0, nullptr, st);
+}
+
+// Measured FP64 FMA throughput of the device: the denominator of the FP64 rooflines (car, hopper).
+// 8 independent dependent-FMA chains per thread, 32 warps per SM, best of 5 launches.
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, double a, double b) {
+  double x[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = threadIdx.x * 1e-9 + i;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = fma(x[i], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += x[i];
+  if (s == 12345.678) out[0] = s;     // never true: keeps the chains alive
+}
+
+int saa_measure_fp64_peak(int device, double *fma_per_s) {
+  if (!fma_per_s) return fail(nullptr, SAA_ERR_ARG, "NULL argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(nullptr, SAA_ERR_NO_DEVICE, "no CUDA device");
+  if (device < 0 || device >= ndev || cudaSetDevice(device) != cudaSuccess) return fail(nullptr, SAA_ERR_ARG, "bad device index");
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(nullptr, SAA_ERR_CUDA, "cudaGetDeviceProperties failed");
+  double *out = nullptr;
+  if (cudaMalloc(&out, 8) != cudaSuccess) return fail(nullptr, SAA_ERR_CUDA, "cudaMalloc failed");
+  const int iters = 2048, blocks = prop.multiProcessorCount * 4;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int rep = 0; rep < 6; ++rep) {
+    cudaEventRecord(e0);
+    fp64_peak_kernel<<<blocks, 256>>>(out, iters, 0.9999999, 1e-7);
+    cudaEventRecord(e1);
+    if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(out); return fail(nullptr, SAA_ERR_CUDA, "fp64 peak kernel failed"); }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+  *fma_per_s = (double)blocks * 256 * iters * 64 / ((double)best * 1e-3);
+  return SAA_OK;
+}
+
+int saa_reserve_sms(saa_handle *h, int n_sms) {
+  if (!h) return fail(h, SAA_ERR_ARG, "NULL handle");
+  if (n_sms < 0 || n_sms >= h->n_sms) return fail(h, SAA_ERR_ARG, "need 0 <= n_sms < number of SMs");
+  h->reserve_sms = n_sms;
+  return SAA_OK;
 }
 
 int saa_check_finite(saa_handle *h, int64_t *count_out, void *stream) {

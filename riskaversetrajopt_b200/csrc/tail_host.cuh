@@ -16,13 +16,19 @@ int launch_drone_means(saa_handle *h, const double *us, void *Z, double *sums, c
   constexpr int kZWarps = 4;
   const int gridz = (int)std::max<i64>(1, std::min<i64>((h->M_local + kZWarps * 32 - 1) / (kZWarps * 32), (i64)h->n_sms * 2));
   const int n = DroneRed<kS>::N;
-  int rc = ensure_scratch(h, (i64)3 * gridz * n);
-  if (rc) return rc;
+  // own scratch: this pass may run on a side stream while an assemble launch uses d_partials
+  const i64 need = (i64)3 * gridz * n;
+  if (h->means_scratch_len < need) {
+    if (h->d_means_scratch) cudaFree(h->d_means_scratch);
+    h->d_means_scratch = nullptr; h->means_scratch_len = 0;
+    SAA_CUDA(h, cudaMalloc(&h->d_means_scratch, need * sizeof(double)));
+    h->means_scratch_len = need;
+  }
   for (int axis = 0; axis < 3; ++axis) {
-    drone_axis_mean_kernel<T, TO, kS, kZWarps><<<gridz, kZWarps * 32, 0, st>>>(A, axis, h->d_partials + (i64)axis * gridz * n);
+    drone_axis_mean_kernel<T, TO, kS, kZWarps><<<gridz, kZWarps * 32, 0, st>>>(A, axis, h->d_means_scratch + (i64)axis * gridz * n);
     SAA_CUDA(h, cudaGetLastError());
   }
-  reduce_partials_kernel<double><<<(n + 3) / 4, 128, 0, st>>>(h->d_partials, 3 * gridz, n, sums);
+  reduce_partials_kernel<double><<<(n + 3) / 4, 128, 0, st>>>(h->d_means_scratch, 3 * gridz, n, sums);
   SAA_CUDA(h, cudaGetLastError());
   if (Z) return launch_drone_rollout<TO>(h, us, nullptr, Z, 0.0, 0.0, 0.0, nullptr, st);
   return SAA_OK;

@@ -52,6 +52,42 @@ def broadcast_controls(us_mat, src=0, group=None, device=None):
     return t.cpu().numpy()
 
 
+class OverlappedMeans:
+    """Sample-mean sums on a side stream, overlapped with the assemble kernel.
+
+    The assemble launch is a persistent grid that saturates HBM for ~2 ms; the all-reduce of the
+    123 mean sums it also produces used to run after it, fully exposed (latency + rank skew, ~75 us
+    = 3.7 % of a step at N = 8).  Here the sums come from the three per-axis mean kernels
+    (``saa_linearize_means``: 536 B read per sample, no matrix) launched FIRST on a side stream,
+    followed by the NCCL all-reduce on that stream; the assemble kernel runs meanwhile on the main
+    stream with one SM left free (``saa_reserve_sms``) so that the collective's kernel can be
+    scheduled; ``finalize`` joins the streams and scatters the means."""
+
+    def __init__(self, path, group=None, reserve_sms=1):
+        self.path, self.group = path, group
+        self.side = torch.cuda.Stream(device=path.device)
+        self.sums = torch.zeros_like(path.mean_sums)
+        check(lib.saa_reserve_sms(path.handle, int(reserve_sms)), path.handle)
+
+    def launch(self, us):
+        """Call BEFORE ``path.assemble(..., finalize=False)`` of the same iterate."""
+        import ctypes as C
+        p = self.path
+        main = torch.cuda.current_stream(p.device)
+        self.side.wait_stream(main)
+        with torch.cuda.stream(self.side):
+            check(lib.saa_linearize_means(p.handle, us.ctypes.data, None, self.sums.data_ptr(),
+                                          C.c_void_p(self.side.cuda_stream)), p.handle)
+            dist.all_reduce(self.sums, op=dist.ReduceOp.SUM, group=self.group)
+
+    def finalize(self, b, scp_iter=2):
+        p = self.path
+        torch.cuda.current_stream(p.device).wait_stream(self.side)
+        ptr = lambda t: t.data_ptr() if torch.is_tensor(t) else int(t)
+        check(lib.saa_finalize_means(p.handle, self.sums.data_ptr(), int(scp_iter), ptr(b['Ax']), ptr(b['l']),
+                                     ptr(b['u']), p._stream()), p.handle)
+
+
 def all_reduce_sums(t, group=None):
     """Sum of the per-rank partial sums (the ``mean`` is taken by ``saa_finalize_means``)."""
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
@@ -325,3 +361,101 @@ class ShardedTailAssembler:
 
     def close(self):
         self.shared.close()
+
+
+# --------------------------------------------------------------------------------------------
+# In-run parity self-check of the multi-GPU delivery modes (bench.py, N > 1)
+# --------------------------------------------------------------------------------------------
+def _rel_err(a, b):
+    """max |a - b| / max(|b|, 1e-300) over finite entries; inf if the non-finite patterns differ."""
+    a, b = a.double(), b.double()
+    fin = torch.isfinite(b)
+    if not torch.equal(fin, torch.isfinite(a)) or not torch.equal(a[~fin], b[~fin]):
+        return float('inf')
+    if not bool(fin.any()):
+        return 0.0
+    return float(((a[fin] - b[fin]).abs() / b[fin].abs().clamp_min(1e-300)).max().item())
+
+
+def _sample_runs(Ax, indptr, n_fin_rows, M_mat, sample_pos, nu, indices):
+    """u-column entries of the samples at positions ``sample_pos`` of a matrix with ``M_mat`` samples,
+    concatenated column by column (device tensor)."""
+    out = []
+    for c in range(nu):
+        lo, hi = int(indptr[c]), int(indptr[c + 1])
+        nf = int((indices[lo:min(hi, lo + 4)] < n_fin_rows).sum())
+        L = (hi - lo - nf - 1) // M_mat
+        if L == 0:
+            continue
+        base = lo + nf
+        idx = (base + sample_pos[:, None] * L + torch.arange(L, device=Ax.device)[None, :]).reshape(-1)
+        out.append(Ax[idx])
+    return torch.cat(out)
+
+
+def parity_self_check(make_path, set_params, M, us, scp_iter=2, group=None, modes=None):
+    """Every delivery mode on ``world`` ranks against ONE GPU assembling all ``M`` samples.
+
+    ``make_path(first, count, M_global) -> DevicePath`` with params and samples set (every rank must be
+    able to build any shard, i.e. the samples are generated identically on all ranks).
+    -> {mode: max relative error} (identical on every rank).  GPUTEST runs on one GPU; this makes the
+    multi-GPU gathers verifiable in the driver's own scaling run."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    first, cnt = shard_range(M, world, rank)
+    single = make_path(0, M, M)
+    dev = single.device
+    ref = {k: v.clone() for k, v in single.assemble(us, scp_iter).items() if torch.is_tensor(v)}
+    n_rows_g, _, indptr_g, indices_g = single.pattern(False)
+    nu = single.S * (3 if single.problem == 0 else 2)
+    n_fin = 6 if single.problem == 0 else 4
+    R = single.S * (3 if single.problem == 0 else 1)
+    row_s0_g = n_fin + 1 + M
+    res = {}
+    modes = modes or (('sharded', 'peer', 'nccl') + (('factored',) if single.problem == 0 else ()) + ('tail',))
+    for mode in modes:
+        err = 0.0
+        if mode == 'nccl' and M % world:
+            continue
+        if mode == 'tail':
+            asm = ShardedTailAssembler(make_path(first, cnt, M), margin=0.5,
+                                       mode='factored' if single.problem == 0 else 'peer', group=group)
+            b, idx = asm.step(us, scp_iter)
+            if rank == 0:
+                torch.cuda.synchronize()
+                n_rows_t, _, indptr_t, indices_t = asm.pattern()
+                K = idx.numel()
+                got = _sample_runs(b['Ax'], indptr_t, n_fin, K, torch.arange(K, device=dev), nu, indices_t)
+                want = _sample_runs(ref['Ax'], indptr_g, n_fin, M, idx.to(dev), nu, indices_g)
+                err = max(err, _rel_err(got, want))
+                rows_t = (n_fin + 1 + K + torch.arange(K * R, device=dev))
+                rows_g = (row_s0_g + (idx.to(dev)[:, None] * R + torch.arange(R, device=dev)[None, :]).reshape(-1))
+                err = max(err, _rel_err(b['u'][rows_t], ref['u'][rows_g]))
+                err = max(err, _rel_err(b['u'][:n_fin], ref['u'][:n_fin]), _rel_err(b['l'][:n_fin], ref['l'][:n_fin]))
+            asm.close()
+        else:
+            path = make_path(first, cnt, M)
+            asm = ShardedAssembler(path, mode=mode, group=group)
+            asm.bind_global_params(set_params)
+            b = asm.step(us, scp_iter)
+            torch.cuda.synchronize()
+            dist.barrier(group=group)
+            if mode == 'sharded':
+                _, _, indptr_s, indices_s = path.pattern(False)
+                got = _sample_runs(b['Ax'], indptr_s, n_fin, cnt, torch.arange(cnt, device=dev), nu, indices_s)
+                want = _sample_runs(ref['Ax'], indptr_g, n_fin, M, first + torch.arange(cnt, device=dev), nu, indices_g)
+                err = max(err, _rel_err(got, want))
+                rs = n_fin + 1 + cnt
+                err = max(err, _rel_err(b['u'][rs:rs + cnt * R], ref['u'][row_s0_g + first * R:row_s0_g + (first + cnt) * R]))
+                err = max(err, _rel_err(b['u'][:n_fin], ref['u'][:n_fin]), _rel_err(b['l'][:n_fin], ref['l'][:n_fin]))
+            elif rank == 0:
+                for k in ('Ax', 'l', 'u'):
+                    err = max(err, _rel_err(b[k], ref[k]))
+            if mode in ('peer', 'factored'):
+                asm.shared.close()
+            del asm, path
+        t = torch.tensor([err], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        res[mode] = float(t.item())
+        torch.cuda.synchronize()
+        dist.barrier(group=group)
+    return res

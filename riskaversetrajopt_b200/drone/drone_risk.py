@@ -29,7 +29,9 @@ OSQP_TOL, OSQP_POLISH = drone_params.OSQP_TOL, drone_params.OSQP_POLISH
 
 class Model:
     def __init__(self, S, DWs, masses, obs_Qs, method='saa', alpha=0.1, *,
-                 variant='risk', precision='fp64', device=None, verbose=False):
+                 variant='risk', precision='fp64', device=None, verbose=False, shard=None):
+        """``shard=(M_global, sample_offset)``: these samples are one rank's block of a sharded set
+        (``riskaversetrajopt_b200.dist``); the matrices then describe the rank's own row block."""
         if verbose:
             print("Initializing Model with")
             print("> method =", method)
@@ -43,8 +45,11 @@ class Model:
         self.DWs, self.masses, self.obs_Qs = DWs, masses, obs_Qs
         self.M = int(np.shape(masses)[0])
         self.variant = variant
-        self.path = DevicePath(_lib.SAA_DRONE, method, self.S, alpha, self.M, variant=variant,
-                               precision=precision, device=device)
+        M_global, sample_offset = (self.M, 0) if shard is None else shard
+        self.path = DevicePath(_lib.SAA_DRONE, method, self.S, alpha, self.M, M_global=M_global,
+                               sample_offset=sample_offset, variant=variant, precision=precision, device=device)
+        if shard is not None:
+            self.path.set_output_geometry(self.M, 0)
         self.path.set_params_drone(drone_params, OSQP_TOL)
         self.path.set_samples_drone(masses, DWs, obs_Qs)
         self.osqp_prob = None

@@ -93,21 +93,14 @@ class TailSubproblem:
         QP variables: (u, y[idx], slack, t)."""
         s = self.sub
         b = self.assemble(us_mat, scp_iter)
-        key = s._uses_relaxed_pattern(scp_iter)
-        outs = []
-        for name in ('Ax', 'l', 'u'):
-            h = s._pinned_like((name, key), b[name])
-            h.copy_(b[name], non_blocking=True)
-            outs.append(h)
-        idx = self.idx.cpu().numpy()              # synchronises the stream
-        arrs = [h.numpy() for h in outs]
-        if s.bits == 32:
-            arrs = [a.astype(np.float64) for a in arrs]
-        elif copy:
-            arrs = [a.copy() for a in arrs]
-        n_rows, n_cols, indptr, indices = s.pattern(key)
-        A = sp.csc_matrix((arrs[0], indices, indptr), shape=(n_rows, n_cols), copy=False)
-        return A, arrs[1], arrs[2], idx
+        # the constant entries (y / slack / t columns, constant bounds) do not depend on WHICH samples
+        # were selected, so after the first call only the iterate-dependent slices cross PCIe
+        A, l, u = s.csc(us_mat, scp_iter, copy=copy, assembled=b)
+        idx = self.idx.cpu().numpy()
+        return A, l, u, idx
+
+    def d2h_bytes_per_call(self, scp_iter=2):
+        return self.sub.d2h_bytes_per_call(scp_iter) + 8 * self.K
 
     def get_objective_coeffs(self, P_full, q_full):
         """Restrict the full problem's (P, q) to the variables (u, y[idx], slack, t).  The y block of
