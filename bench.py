@@ -328,14 +328,13 @@ def run_ours(args):
     us = bench_us()
     scp_iter = 2
     stream = torch.cuda.current_stream(device)
-    overlap = sd.OverlappedMeans(path) if world > 1 else None
+    peer = sd.PeerMeans(path) if world > 1 else None
 
     def step():
         if world == 1:
             return path.assemble(us, scp_iter, finalize=True)
-        overlap.launch(us)                               # mean kernels + NCCL all-reduce, side stream
         b = path.assemble(us, scp_iter, finalize=False, write_shared=True)
-        overlap.finalize(b, scp_iter)
+        peer.finalize(b, scp_iter)                       # all-reduce + mean rows in one launch over NVLink
         return b
 
     def barrier():
@@ -385,9 +384,8 @@ def run_ours(args):
             if world == 1:
                 return model.get_constraints_coeffs(us, scp_iter, copy=False)     # THE drop-in boundary
             # sharded: the expectation rows need the all-reduced sums, then the same host delivery
-            overlap.launch(us)
             b = path.assemble(us, scp_iter, finalize=False, write_shared=True)
-            overlap.finalize(b, scp_iter)
+            peer.finalize(b, scp_iter)
             return path.csc(us, scp_iter, copy=False, assembled=b)
 
         A, l, u = e2e_step()                             # first call: pinned allocation + full copy
@@ -438,7 +436,8 @@ def run_ours(args):
     # ---- N > 1: delivery modes at M = 10^6 in total, and their parity against one GPU ------------
     target = parity = None
     if world > 1:
-        del model, path, overlap
+        peer.close()
+        del model, path, peer
         torch.cuda.empty_cache()
         if not args.no_parity:
             try:
@@ -463,9 +462,8 @@ def run_ours(args):
             cpu = cpu_port_baseline()
         except Exception as exc:
             cpu = {"value": None, "unit": UNIT, "error": repr(exc)[:200]}
-    # drone_assemble + drone_axis_mean + reduce_partials + scatter_means; N > 1: + 3 axis-mean kernels and their
-    # reduce on the side stream (the NCCL all-reduce kernel is not ours)
-    launches_per_step = 4 if world == 1 else 8
+    # drone_assemble + drone_axis_mean + reduce_partials + (scatter_means | peer_allreduce_finalize)
+    launches_per_step = 4
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -474,8 +472,8 @@ def run_ours(args):
                    "samples_per_gpu": M, "samples_total": M_global, "alpha": 0.1, "scp_iter": scp_iter,
                    "method": "saa", "l2": "per-step output 9.6 GB/GPU >> 126 MB L2 (no flush needed)",
                    "row_blocks": "sharded (each rank keeps its block in HBM)" if world > 1 else "single GPU",
-                   "collective": "all_reduce(123 f64) per step on a side stream, overlapped with the assemble kernel "
-                                 "(1 SM reserved for it)" if world > 1 else "none"},
+                   "collective": "all-reduce of the 123 mean sums fused with their finalisation: one kernel over NVLink "
+                                 "peer memory per step (saa_peer_allreduce_finalize)" if world > 1 else "none"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": _traffic(), "peak_source": peak_src,
                      "kernel": "drone_assemble_kernel<double,double,20,6,FULL>", "kernel_ms": kernel_ms,

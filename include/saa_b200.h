@@ -177,6 +177,21 @@ int saa_finalize_means(saa_handle *h, const double *mean_sums_dev, int scp_iter,
                        void *Ax_dev, void *l_dev, void *u_dev, void *stream);
 
 /*
+ * Fused all-reduce + finalize over NVLink peer memory (alternative to ncclAllReduce +
+ * saa_finalize_means; <= 16 ranks of one box).  Every rank allocates an inbox of
+ * saa_peer_inbox_bytes() with saa_shared_alloc (zero-initialised) and maps the others' with
+ * saa_shared_open; inboxes_host[q] is rank q's inbox as seen from this rank.  One launch per
+ * iteration on every rank with the same `epoch` (1, 2, 3, ...): the kernel stores this rank's
+ * mean_sums into all inboxes, waits for all ranks' contributions, adds them IN RANK ORDER and
+ * scatters mean = sum / M_global into Ax / l / u -- a few microseconds of NVLink latency, and
+ * bitwise identical expectation rows on every rank.
+ * replaces: jnp.mean(...) drone/drone_risk.py:294-300, car/driving.py:311-317 across ranks.    */
+int64_t saa_peer_inbox_bytes(void);
+int saa_peer_allreduce_finalize(saa_handle *h, const double *mean_sums_dev, int scp_iter,
+                                void *Ax_dev, void *l_dev, void *u_dev, int rank, int world,
+                                void *const *inboxes_host, uint64_t epoch, void *stream);
+
+/*
  * Multi-GPU gather, NCCL variant: after the ranks' compact value blocks (a matrix of
  * M_shard samples each, i.e. what saa_linearize_assemble writes under
  * saa_set_output_geometry(M_shard, 0)) have been gathered into rank 0's memory,

@@ -90,6 +90,9 @@ _PROTOTYPES = {
     "saa_check_finite": (C.c_int, [_H, C.POINTER(C.c_int64), C.c_void_p]),
     "saa_measure_fp64_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
     "saa_reserve_sms": (C.c_int, [_H, C.c_int]),
+    "saa_peer_inbox_bytes": (C.c_int64, []),
+    "saa_peer_allreduce_finalize": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                              C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_uint64, C.c_void_p]),
     "saa_hopper_g": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "saa_hopper_jac": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p]),
     "saa_hopper_g_jac": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

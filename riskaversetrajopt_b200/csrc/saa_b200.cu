@@ -366,6 +366,52 @@ int launch_finalize(saa_handle *h, const double *sums, int relaxed_pattern, void
 }
 
 // ---------------------------------------------------------------------------
+// Fused all-reduce + finalize over NVLink peer memory (multi-GPU).  Every rank owns an inbox
+//   struct { double data[2][W][128]; unsigned long long flag[W]; }
+// mapped by all the others (CUDA IPC).  One 128-thread block per rank: store my sums into slot
+// [epoch & 1][rank] of EVERY inbox (peer stores), fence, raise flag[rank] = epoch in every inbox, spin
+// until my own inbox holds the epoch of every rank, then add the W contributions in rank order and
+// scatter the means.  One launch, a few microseconds of NVLink latency, no NCCL kernel -- and because
+// every rank adds the same numbers in the same order, the expectation rows are bitwise identical on
+// all ranks and independent of arrival order.  The double buffer makes epoch e+1 writes safe while a
+// slow rank still reads epoch e (a rank cannot run two epochs ahead: it needs the slow rank's flag).
+// ---------------------------------------------------------------------------
+constexpr int kPeerSlots = 128, kPeerMaxWorld = 16;
+struct PeerInbox { double data[2][kPeerMaxWorld][kPeerSlots]; unsigned long long flag[kPeerMaxWorld]; };
+struct PeerArgs { PeerInbox *inbox[kPeerMaxWorld]; int rank, world; unsigned long long epoch; };
+
+template <typename T>
+__global__ void __launch_bounds__(kPeerSlots)
+peer_allreduce_finalize_kernel(const __grid_constant__ PeerArgs P, const double *__restrict__ sums, double inv_M,
+                               int n_entries, const i64 *__restrict__ fin_off, int n_fin, T *Ax, T *l, T *u) {
+  const int r = threadIdx.x, n = n_entries + n_fin, par = (int)(P.epoch & 1);
+  if (r < n) {
+    const double v = sums[r];
+    for (int q = 0; q < P.world; ++q) {
+      volatile double *dst = &P.inbox[q]->data[par][P.rank][r];
+      *dst = v;
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (r < P.world) {
+    volatile unsigned long long *f = &P.inbox[r]->flag[P.rank];
+    *f = P.epoch;
+    volatile unsigned long long *mine = &P.inbox[P.rank]->flag[r];
+    while (*mine < P.epoch) { }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (r < n) {
+    double acc = 0.0;
+    for (int p = 0; p < P.world; ++p) acc += ((volatile double *)P.inbox[P.rank]->data[par][p])[r];
+    const T v = (T)(acc * inv_M);
+    if (r < n_entries) Ax[fin_off[r]] = v;
+    else { l[r - n_entries] = v; u[r - n_entries] = v; }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // merge a gathered compact shard into the destination matrix (multi-GPU, NCCL path)
 // ---------------------------------------------------------------------------
 struct MergeArgs {
@@ -632,6 +678,37 @@ int saa_linearize_assemble(saa_handle *h, const double *us, int scp_iter, void *
   return SAA_OK;
 }
 
+int64_t saa_peer_inbox_bytes(void) { return (int64_t)sizeof(PeerInbox); }
+
+int saa_peer_allreduce_finalize(saa_handle *h, const double *sums, int scp_iter, void *Ax, void *l, void *u,
+                                int rank, int world, void *const *inboxes, uint64_t epoch, void *stream) {
+  if (!h || !sums || !Ax || !l || !u || !inboxes) return fail(h, SAA_ERR_ARG, "NULL argument");
+  if (h->problem == SAA_HOPPER) return fail(h, SAA_ERR_ARG, "hopper has no mean rows");
+  if (world < 1 || world > kPeerMaxWorld || rank < 0 || rank >= world) return fail(h, SAA_ERR_ARG, "bad rank / world (<= 16 ranks)");
+  if (epoch == 0) return fail(h, SAA_ERR_ARG, "epochs start at 1");
+  SAA_CUDA(h, cudaSetDevice(h->device));
+  PeerArgs P{};
+  for (int q = 0; q < world; ++q) {
+    if (!inboxes[q]) return fail(h, SAA_ERR_ARG, "NULL inbox pointer");
+    P.inbox[q] = (PeerInbox *)inboxes[q];
+  }
+  P.rank = rank; P.world = world; P.epoch = epoch;
+  const int n_entries = (int)saa_mean_len(h) - h->lay.n_fin, n = n_entries + h->lay.n_fin;
+  if (n > kPeerSlots) return fail(h, SAA_ERR_STATE, "internal: mean block larger than the inbox slots");
+  const bool relaxed_pattern = h->problem == SAA_CAR && scp_iter < 1;
+  const i64 *fin_off = h->d_fin_off + (relaxed_pattern ? 256 : 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  const double inv_M = 1.0 / (double)h->M_global;
+  if (h->precision == 64)
+    peer_allreduce_finalize_kernel<double><<<1, kPeerSlots, 0, st>>>(P, sums, inv_M, n_entries, fin_off, h->lay.n_fin,
+                                                                    (double *)Ax, (double *)l, (double *)u);
+  else
+    peer_allreduce_finalize_kernel<float><<<1, kPeerSlots, 0, st>>>(P, sums, inv_M, n_entries, fin_off, h->lay.n_fin,
+                                                                   (float *)Ax, (float *)l, (float *)u);
+  SAA_CUDA(h, cudaGetLastError());
+  return SAA_OK;
+}
+
 int saa_merge_shard(saa_handle *h, const void *shard_Ax, const void *shard_u, int64_t M_shard,
                     int64_t first, void *Ax, void *u, void *stream) {
   if (!h || !shard_Ax || !shard_u || !Ax || !u) return fail(h, SAA_ERR_ARG, "NULL argument");
@@ -651,6 +728,7 @@ int saa_shared_alloc(int device, int64_t bytes, void **ptr_out, unsigned char ha
   void *p = nullptr;
   cudaError_t e = cudaMalloc(&p, (size_t)bytes);
   if (e != cudaSuccess) return fail(nullptr, SAA_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  if (bytes <= (1 << 20)) cudaMemset(p, 0, (size_t)bytes);     // small control blocks (peer inboxes) start zeroed
   cudaIpcMemHandle_t hd;
   e = cudaIpcGetMemHandle(&hd, p);
   if (e != cudaSuccess) { cudaFree(p); return fail(nullptr, SAA_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e)); }

@@ -52,40 +52,61 @@ def broadcast_controls(us_mat, src=0, group=None, device=None):
     return t.cpu().numpy()
 
 
-class OverlappedMeans:
-    """Sample-mean sums on a side stream, overlapped with the assemble kernel.
+class PeerMeans:
+    """All-reduce of the sample-mean sums fused with their finalisation, over NVLink peer memory.
 
-    The assemble launch is a persistent grid that saturates HBM for ~2 ms; the all-reduce of the
-    123 mean sums it also produces used to run after it, fully exposed (latency + rank skew, ~75 us
-    = 3.7 % of a step at N = 8).  Here the sums come from the three per-axis mean kernels
-    (``saa_linearize_means``: 536 B read per sample, no matrix) launched FIRST on a side stream,
-    followed by the NCCL all-reduce on that stream; the assemble kernel runs meanwhile on the main
-    stream with one SM left free (``saa_reserve_sms``) so that the collective's kernel can be
-    scheduled; ``finalize`` joins the streams and scatters the means."""
+    ``ncclAllReduce(123 f64)`` + ``saa_finalize_means`` cost ~75 us per step at N = 8 (collective
+    latency + a second launch, serialised behind the 1.9 ms assemble kernel whose last block
+    produces the sums).  ``saa_peer_allreduce_finalize`` is ONE launch: every rank stores its sums
+    into every rank's inbox with peer stores, raises a flag, waits for the others' flags and adds the
+    contributions in rank order -- a few microseconds, deterministic, bitwise identical on all ranks.
+    (Running the means on a side stream instead does not work: the assemble kernel is a persistent
+    grid that owns every register file, measured +0.16 ms.)"""
 
-    def __init__(self, path, group=None, reserve_sms=1):
-        self.path, self.group = path, group
-        self.side = torch.cuda.Stream(device=path.device)
-        self.sums = torch.zeros_like(path.mean_sums)
-        check(lib.saa_reserve_sms(path.handle, int(reserve_sms)), path.handle)
-
-    def launch(self, us):
-        """Call BEFORE ``path.assemble(..., finalize=False)`` of the same iterate."""
+    def __init__(self, path, group=None):
         import ctypes as C
-        p = self.path
-        main = torch.cuda.current_stream(p.device)
-        self.side.wait_stream(main)
-        with torch.cuda.stream(self.side):
-            check(lib.saa_linearize_means(p.handle, us.ctypes.data, None, self.sums.data_ptr(),
-                                          C.c_void_p(self.side.cuda_stream)), p.handle)
-            dist.all_reduce(self.sums, op=dist.ReduceOp.SUM, group=self.group)
+        self.path, self.group = path, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        nbytes = int(lib.saa_peer_inbox_bytes())
+        dev = path.device.index
+        ptr, hd = C.c_void_p(), C.create_string_buffer(64)
+        check(lib.saa_shared_alloc(dev, nbytes, C.byref(ptr), hd))
+        self._own = ptr.value
+        handles = [None] * self.world
+        dist.all_gather_object(handles, hd.raw, group=group)
+        self._ptrs = (C.c_void_p * self.world)()
+        self._opened = []
+        for q, raw in enumerate(handles):
+            if q == self.rank:
+                self._ptrs[q] = self._own
+            else:
+                p = C.c_void_p()
+                check(lib.saa_shared_open(dev, raw, C.byref(p)))
+                self._ptrs[q] = p.value
+                self._opened.append(p.value)
+        self.epoch = 0
+        dist.barrier(group=group)
 
     def finalize(self, b, scp_iter=2):
+        """After ``path.assemble(..., finalize=False)`` on the same stream, on EVERY rank."""
         p = self.path
-        torch.cuda.current_stream(p.device).wait_stream(self.side)
+        self.epoch += 1
         ptr = lambda t: t.data_ptr() if torch.is_tensor(t) else int(t)
-        check(lib.saa_finalize_means(p.handle, self.sums.data_ptr(), int(scp_iter), ptr(b['Ax']), ptr(b['l']),
-                                     ptr(b['u']), p._stream()), p.handle)
+        check(lib.saa_peer_allreduce_finalize(p.handle, p.mean_sums.data_ptr(), int(scp_iter), ptr(b['Ax']),
+                                              ptr(b['l']), ptr(b['u']), self.rank, self.world, self._ptrs,
+                                              self.epoch, p._stream()), p.handle)
+
+    def close(self):
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        dev = self.path.device.index
+        for p in self._opened:
+            lib.saa_shared_close(dev, p)
+        self._opened = []
+        dist.barrier(group=self.group)
+        if self._own:
+            lib.saa_shared_free(dev, self._own)
+            self._own = None
 
 
 def all_reduce_sums(t, group=None):
@@ -411,7 +432,8 @@ def parity_self_check(make_path, set_params, M, us, scp_iter=2, group=None, mode
     R = single.S * (3 if single.problem == 0 else 1)
     row_s0_g = n_fin + 1 + M
     res = {}
-    modes = modes or (('sharded', 'peer', 'nccl') + (('factored',) if single.problem == 0 else ()) + ('tail',))
+    modes = modes or (('sharded', 'sharded_peer_means', 'peer', 'nccl') + (('factored',) if single.problem == 0 else ())
+                      + ('tail',))
     for mode in modes:
         err = 0.0
         if mode == 'nccl' and M % world:
@@ -432,6 +454,29 @@ def parity_self_check(make_path, set_params, M, us, scp_iter=2, group=None, mode
                 err = max(err, _rel_err(b['u'][rows_t], ref['u'][rows_g]))
                 err = max(err, _rel_err(b['u'][:n_fin], ref['u'][:n_fin]), _rel_err(b['l'][:n_fin], ref['l'][:n_fin]))
             asm.close()
+        elif mode == 'sharded_peer_means':
+            # row blocks stay sharded; the expectation rows come from the fused peer-memory all-reduce
+            path = make_path(first, cnt, M)
+            path.set_output_geometry(cnt, 0)
+            pm = PeerMeans(path, group=group)
+            for _ in range(3):                           # several epochs: flags / double buffer
+                b = path.assemble(us, scp_iter, finalize=False)
+                pm.finalize(b, scp_iter)
+            torch.cuda.synchronize()
+            err = max(err, _rel_err(b['u'][:n_fin], ref['u'][:n_fin]), _rel_err(b['l'][:n_fin], ref['l'][:n_fin]))
+            _, _, indptr_s, indices_s = path.pattern(False)
+            fin_s = torch.as_tensor(np.flatnonzero(indices_s[:int(indptr_s[nu])] < n_fin), device=dev)
+            fin_g = torch.as_tensor(np.flatnonzero(indices_g[:int(indptr_g[nu])] < n_fin), device=dev)
+            err = max(err, _rel_err(b['Ax'][fin_s], ref['Ax'][fin_g]))
+            # bitwise identical on every rank (same numbers added in the same order)
+            mine = torch.cat([b['l'][:n_fin].double(), b['Ax'][fin_s].double()])
+            lo, hi = mine.clone(), mine.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+            if not torch.equal(lo, hi):
+                err = float('inf')
+            pm.close()
+            del path
         else:
             path = make_path(first, cnt, M)
             asm = ShardedAssembler(path, mode=mode, group=group)
