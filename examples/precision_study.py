@@ -45,8 +45,9 @@ def main():
     scale = float(a["Ax"].abs().max())
     out["M"] = M
     out["max_abs_err_Ax_over_max_abs_Ax"] = float((a["Ax"] - f["Ax"]).abs().max()) / scale
-    big = a["Ax"].abs() > 1e-3 * scale
-    out["max_rel_err_Ax_entries_above_1e-3_of_max"] = float(((a["Ax"] - f["Ax"]).abs()[big] / a["Ax"].abs()[big]).max())
+    nz = a["Ax"] != 0
+    out["max_rel_err_Ax_per_entry_all_nonzero_entries"] = float(((a["Ax"] - f["Ax"]).abs()[nz] / a["Ax"].abs()[nz]).max())
+    out["fp32_mode"] = "FP32 storage of the outputs, FP64 arithmetic (include/saa_b200.h): each entry is the FP64 entry rounded once"
     fin = torch.isfinite(a["u"])
     out["max_abs_err_u"] = float((a["u"][fin] - f["u"][fin]).abs().max())
     out["max_abs_err_mean_rows_l"] = float((a["l6"] - f["l6"]).abs().max())

@@ -117,6 +117,8 @@ int saa_pattern_sizes(const saa_handle *h, int relaxed_pattern,
                       int64_t *n_rows, int64_t *n_cols, int64_t *nnz);
 int saa_pattern_i32(const saa_handle *h, int relaxed_pattern,
                     int32_t *indptr_host, int32_t *indices_host);
+/* indices_host may be NULL in the _i64 variants: only the column pointers are written (the row
+ * indices of a 10^6-sample matrix are 10+ GB; the runs are closed-form).        */
 int saa_pattern_i64(const saa_handle *h, int relaxed_pattern,
                     int64_t *indptr_host, int64_t *indices_host);
 

@@ -191,7 +191,7 @@ class CarOracleB:
         self.w_s = np.asarray(omegas_speed, dtype=np.float64)
         self.w_r = np.asarray(omegas_repulsive, dtype=np.float64)
         self.DWs = np.asarray(DWs, dtype=np.float64)
-        self.M, self.S, self.dt, self.beta = self.w_s.shape[0], cp.S, cp.dt, 3e-2
+        self.M, self.S, self.dt, self.beta = self.w_s.shape[0], int(np.shape(DWs)[1]), cp.dt, 3e-2   # S: horizon of the noise array (cp.S = 20 in the reference)
 
     def rollout(self, us_mat, with_jac=False):
         S, dt, M = self.S, self.dt, self.M

@@ -442,8 +442,9 @@ def reshape(a, shape, order='C'):
 
 def repeat(a, repeats, axis=None):
     a = _as_arr(a)
-    if axis is None:
-        raise NotImplementedError("repeat: axis required")
+    if axis is None:                                   # flattened, like numpy
+        a = reshape(a, (-1,))
+        axis = 0
     ax = _axis(axis, a.ndim)
     return Arr(np.repeat(a.val, repeats, axis=ax),
                None if a.tan is None else np.repeat(a.tan, repeats, axis=ax))

@@ -95,7 +95,7 @@ struct CarRelaxArgs {
   int nu, keep_y, keep_s, saa, n_x, R;
   i64 ycol0, slackcol, tcol, row_cvar, row_y0, row_s0, row_ctrl0;
   double cvar_t, u_max;
-  i64 ucol_last[64];
+  i64 ucol_last[128];
 };
 
 template <typename T>

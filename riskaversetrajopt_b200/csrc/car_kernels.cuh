@@ -463,6 +463,9 @@ __device__ __forceinline__ void car_rollout_pass(const CarArgs<T, TO, S> &A, con
       zmax = fmax(zmax, g);
       if (c == (k & 1)) ubrow[k - 1] = (TO)(gu - g);
     }
+    // rows 3k..3k+2 held noise increments of steps <= (3k + 2 - DWBASE) / 2 < k: every lane has read
+    // them (program order + this barrier; racecheck does not count the shuffle above as one)
+    __syncwarp();
     if (c == 0) { geo[3 * k][si] = nhx; geo[3 * k + 2][si] = om_n; }
     else geo[3 * k + 1][si] = nhy;
     if constexpr (k < S) {

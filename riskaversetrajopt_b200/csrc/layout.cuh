@@ -102,6 +102,18 @@ template <typename I>
 void Layout::fill(I *indptr, I *indices) const {
   int rows[4];
   for (int c = 0; c <= nu; ++c) indptr[c] = (I)ucol[c];
+  if (indices == nullptr) {            // column pointers only (the row indices of 10^6+ samples are tens of GB)
+    if (method != SAA_METHOD_SAA) { for (i64 i = 0; i <= M + 1; ++i) indptr[nu + 1 + i] = (I)nnz; return; }
+    if (!relaxed_pattern) {
+      const i64 yl = ycol_len();
+      for (i64 i = 0; i < M; ++i) indptr[nu + i] = (I)(ycol0 + i * yl);
+    } else {
+      i64 pos = ycol0;
+      for (i64 i = 0; i < M; ++i) { indptr[nu + i] = (I)pos; pos += 1 + (i < keep_y) + (i == 0 ? keep_s : 0); }
+    }
+    indptr[nu + M] = (I)slackcol; indptr[nu + M + 1] = (I)tcol; indptr[nu + M + 2] = (I)nnz;
+    return;
+  }
   for (int c = 0; c < nu; ++c) {
     I *out = indices + ucol[c];
     const int nf = fin_rows(c, rows);

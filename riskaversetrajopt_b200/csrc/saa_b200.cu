@@ -11,6 +11,7 @@
 #include "car_kernels.cuh"
 #include "hopper_kernels.cuh"
 #include "tail_kernels.cuh"
+#include "generic_kernels.cuh"
 
 using namespace saa;
 
@@ -166,7 +167,7 @@ struct ConstArgs {
   double l_rows, u_cvar, u_y, u_slack;      // bounds of the risk rows
   int write_u_rows; double u_rows;          // relaxed: sample-row upper bounds are constant
   double u_max;
-  i64 ucol_last[64];                        // position of the control-identity entry per u column
+  i64 ucol_last[128];                       // position of the control-identity entry per u column
 };
 
 template <typename T>
@@ -213,7 +214,7 @@ template <typename T>
 int launch_constants(saa_handle *h, int scp_iter, int write_shared, void *Ax, void *l, void *u,
                      cudaStream_t st) {
   const Layout &L = h->lay;
-  if (L.nu > 64) return fail(h, SAA_ERR_ARG, "n_u*S > 64 unsupported");
+  if (L.nu > 128) return fail(h, SAA_ERR_ARG, "n_u*S > 128 unsupported");
   ConstArgs C{};
   C.M_local = h->M_local; C.first_out = h->first_out; C.M_out = h->M_out;
   C.R = L.R; C.nu = L.nu; C.n_fin = L.n_fin;
@@ -459,9 +460,12 @@ int launch_merge(saa_handle *h, const void *sAx, const void *su, i64 M_shard, i6
 
 }  // namespace
 
+int64_t saa_mean_len(const saa_handle *h);
+
 #include "car_host.cuh"
 #include "hopper_host.cuh"
 #include "tail_host.cuh"
+#include "generic_host.cuh"
 
 // =============================================================================
 // C ABI
@@ -482,8 +486,9 @@ int saa_create(saa_handle **out, int problem, int method, int variant, int64_t M
   if (precision != 64 && precision != 32) return fail(nullptr, SAA_ERR_ARG, "precision must be 64 or 32");
   if (M_local <= 0 || M_global < M_local || sample_offset < 0 || sample_offset + M_local > M_global)
     return fail(nullptr, SAA_ERR_ARG, "need 0 < M_local <= M_global and the local range inside the global one");
-  if (problem != SAA_HOPPER && S != kS)
-    return fail(nullptr, SAA_ERR_ARG, "this build instantiates the kernels for S = 20 (the reference horizon)");
+  if (problem != SAA_HOPPER && (S < 3 || S > kGenSMax))
+    return fail(nullptr, SAA_ERR_ARG, "need 3 <= S <= 32 (S = 20, the reference horizon, runs the tuned kernels; "
+                                      "other horizons the generic ones)");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(nullptr, SAA_ERR_NO_DEVICE, "no CUDA device: libsaa_b200 has no CPU fallback");
@@ -574,7 +579,7 @@ int saa_pattern_i32(const saa_handle *h, int relaxed_pattern, int32_t *indptr, i
 }
 
 int saa_pattern_i64(const saa_handle *h, int relaxed_pattern, int64_t *indptr, int64_t *indices) {
-  if (!h || !indptr || !indices) return fail(h, SAA_ERR_ARG, "NULL argument");
+  if (!h || !indptr) return fail(h, SAA_ERR_ARG, "NULL argument");
   if (h->problem == SAA_HOPPER) return fail(h, SAA_ERR_ARG, "hopper has no QP pattern");
   Layout L; L.build(h->problem, h->method, h->S, h->M_out, relaxed_pattern != 0);
   L.fill<int64_t>(indptr, indices);
@@ -612,7 +617,7 @@ int saa_static_pattern_i32(int problem, int method, int S, int64_t M, int relaxe
 int saa_static_pattern_i64(int problem, int method, int S, int64_t M, int relaxed_pattern,
                            int64_t *indptr, int64_t *indices) {
   if (int rc = static_args_ok(problem, method, S, M)) return rc;
-  if (!indptr || !indices) return fail(nullptr, SAA_ERR_ARG, "NULL argument");
+  if (!indptr) return fail(nullptr, SAA_ERR_ARG, "NULL argument");
   Layout L; L.build(problem, method, S, M, relaxed_pattern != 0);
   L.fill<int64_t>(indptr, indices);
   return SAA_OK;
@@ -640,8 +645,8 @@ int saa_write_constants(saa_handle *h, int scp_iter, int write_shared, void *Ax,
 
 int64_t saa_mean_len(const saa_handle *h) {
   if (!h) return 0;
-  if (h->problem == SAA_DRONE) return DroneRed<kS>::N;
-  if (h->problem == SAA_CAR) return CarRed<kS>::N;
+  if (h->problem == SAA_DRONE) return GenDroneRed{h->S}.n();     // == DroneRed<S>::N
+  if (h->problem == SAA_CAR) return GenCarRed{h->S}.n();         // == CarRed<S>::N
   return 0;
 }
 
@@ -666,7 +671,15 @@ int saa_linearize_assemble(saa_handle *h, const double *us, int scp_iter, void *
   int rc = ensure_scratch(h, 1);
   if (rc) return rc;
   double *sums = mean_sums ? mean_sums : h->d_sums;
-  if (h->problem == SAA_DRONE)
+  if (h->S != kS) {
+    // horizon-generic kernels (generic_kernels.cuh)
+    if (h->problem == SAA_DRONE)
+      rc = h->precision == 64 ? launch_drone_generic<double>(h, us, scp_iter, Ax, u, Z, sums, st)
+                              : launch_drone_generic<float>(h, us, scp_iter, Ax, u, Z, sums, st);
+    else
+      rc = h->precision == 64 ? launch_car_generic<double>(h, us, scp_iter, Ax, u, Z, sums, st)
+                              : launch_car_generic<float>(h, us, scp_iter, Ax, u, Z, sums, st);
+  } else if (h->problem == SAA_DRONE)
     rc = h->precision == 64
              ? launch_drone_assemble<double, DRONE_FULL>(h, us, scp_iter, Ax, u, Z, nullptr, nullptr, 0, 0, sums, st)
              : launch_drone_assemble<float, DRONE_FULL>(h, us, scp_iter, Ax, u, Z, nullptr, nullptr, 0, 0, sums, st);
@@ -761,7 +774,7 @@ int saa_shared_free(int device, void *ptr) {
 
 int saa_factored_sizes(const saa_handle *h, int64_t *n_sp, int64_t *n_p) {
   if (!h) return fail(h, SAA_ERR_ARG, "NULL handle");
-  if (h->problem != SAA_DRONE) return fail(h, SAA_ERR_ARG, "the factored record is implemented for the drone");
+  if (h->problem != SAA_DRONE || h->S != kS) return fail(h, SAA_ERR_ARG, "the factored record is implemented for the drone at S = 20");
   if (n_sp) *n_sp = h->M_out * (i64)(kS * (kS - 1));              // 2 axes x S(S-1)/2 sensitivities
   if (n_p) *n_p = h->M_out * (i64)(2 * DroneFac<kS>::ROWS);
   return SAA_OK;
@@ -770,7 +783,7 @@ int saa_factored_sizes(const saa_handle *h, int64_t *n_sp, int64_t *n_p) {
 int saa_linearize_factored(saa_handle *h, const double *us, int scp_iter, void *fsp, void *fp, void *u,
                            void *Z, double *mean_sums, void *stream) {
   if (!h || !us || !fsp || !fp || !u) return fail(h, SAA_ERR_ARG, "NULL argument");
-  if (h->problem != SAA_DRONE) return fail(h, SAA_ERR_ARG, "the factored record is implemented for the drone");
+  if (h->problem != SAA_DRONE || h->S != kS) return fail(h, SAA_ERR_ARG, "the factored record is implemented for the drone at S = 20");
   if (!h->params_set || !h->samples_set) return fail(h, SAA_ERR_STATE, "set params and samples first");
   SAA_CUDA(h, cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
@@ -785,7 +798,7 @@ int saa_linearize_factored(saa_handle *h, const double *us, int scp_iter, void *
 int saa_expand_factored(saa_handle *h, int scp_iter, const void *fsp, const void *fp, int64_t sample_begin,
                         int64_t sample_count, void *Ax, void *stream) {
   if (!h || !fsp || !fp || !Ax) return fail(h, SAA_ERR_ARG, "NULL argument");
-  if (h->problem != SAA_DRONE) return fail(h, SAA_ERR_ARG, "the factored record is implemented for the drone");
+  if (h->problem != SAA_DRONE || h->S != kS) return fail(h, SAA_ERR_ARG, "the factored record is implemented for the drone at S = 20");
   if (!h->params_set) return fail(h, SAA_ERR_STATE, "set params first");
   if (sample_begin < 0 || sample_count < 0 || sample_begin + sample_count > h->M_out)
     return fail(h, SAA_ERR_ARG, "sample range outside the output geometry");
@@ -805,6 +818,13 @@ int saa_rollout(saa_handle *h, const double *us, void *Xs, void *stream) {
   if (!h->params_set || !h->samples_set) return fail(h, SAA_ERR_STATE, "set params and samples first");
   SAA_CUDA(h, cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
+  if (h->S != kS) {
+    if (h->problem == SAA_DRONE)
+      return h->precision == 64 ? launch_drone_generic_rollout<double>(h, us, Xs, nullptr, 0, 0, 0, nullptr, st)
+                                : launch_drone_generic_rollout<float>(h, us, Xs, nullptr, 0, 0, 0, nullptr, st);
+    return h->precision == 64 ? launch_car_generic_rollout<double>(h, us, Xs, nullptr, 0, 0, 0, nullptr, st)
+                              : launch_car_generic_rollout<float>(h, us, Xs, nullptr, 0, 0, 0, nullptr, st);
+  }
   if (h->problem == SAA_DRONE)
     return h->precision == 64 ? launch_drone_rollout<double>(h, us, Xs, nullptr, 0, 0, 0, nullptr, st)
                               : launch_drone_rollout<float>(h, us, Xs, nullptr, 0, 0, 0, nullptr, st);
@@ -888,6 +908,14 @@ int saa_cvar_terms(saa_handle *h, const double *us, double t_risk, double sat_to
   if (!h->params_set || !h->samples_set) return fail(h, SAA_ERR_STATE, "set params and samples first");
   SAA_CUDA(h, cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
+  if (h->S != kS) {
+    const double tol = h->problem == SAA_DRONE ? h->dp.osqp_tol : h->cp.osqp_tol;
+    if (h->problem == SAA_DRONE)
+      return h->precision == 64 ? launch_drone_generic_rollout<double>(h, us, nullptr, Z, t_risk, sat_tol, tol, out3, st)
+                                : launch_drone_generic_rollout<float>(h, us, nullptr, Z, t_risk, sat_tol, tol, out3, st);
+    return h->precision == 64 ? launch_car_generic_rollout<double>(h, us, nullptr, Z, t_risk, sat_tol, tol, out3, st)
+                              : launch_car_generic_rollout<float>(h, us, nullptr, Z, t_risk, sat_tol, tol, out3, st);
+  }
   if (h->problem == SAA_DRONE) {
     const double tol = h->dp.osqp_tol;
     return h->precision == 64 ? launch_drone_rollout<double>(h, us, nullptr, Z, t_risk, sat_tol, tol, out3, st)

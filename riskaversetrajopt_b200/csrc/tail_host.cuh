@@ -98,6 +98,7 @@ int saa_linearize_means(saa_handle *h, const double *us, void *Z, double *mean_s
   if (!h || !us || !mean_sums) return fail(h, SAA_ERR_ARG, "NULL argument");
   if (h->problem == SAA_HOPPER) return fail(h, SAA_ERR_ARG, "the hopper has no expectation rows");
   if (!h->params_set || !h->samples_set) return fail(h, SAA_ERR_STATE, "set params and samples first");
+  if (h->S != kS) return fail(h, SAA_ERR_ARG, "the means-only pass (tail-reduced subproblem) is implemented for S = 20");
   SAA_CUDA(h, cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
   if (h->problem == SAA_DRONE)

@@ -73,6 +73,21 @@ def drone(dest=HERE):
                 out[k + "_data"], out[k + "_l"], out[k + "_u"] = A.data, l, u
     np.savez_compressed(os.path.join(dest, "ref_drone_M8_branches.npz"), **out)
 
+    # another horizon: S is a constructor argument of the reference's Model (:70-83)
+    S12, M6 = 12, 6
+    m.M = M6
+    np.random.seed(7)
+    DWs, masses, obs_Qs = m.sample_uncertain_parameters('saa', M=M6, S=S12, dt=m.T / S12)
+    model = m.Model(S12, DWs, masses, obs_Qs, 'saa', 0.1)
+    us = np.asarray(model.initial_guess_us_mat()) + 0.3 * np.random.RandomState(3).randn(S12, 3)
+    out = dict(us=us, DWs=DWs, masses=masses, obs_Qs=obs_Qs)
+    for it in (0, 2):
+        A, l, u = model.get_constraints_coeffs(jnp.array(us), it)
+        k = f"iter{it}"
+        out[k + "_indptr"], out[k + "_indices"], out[k + "_data"], out[k + "_l"], out[k + "_u"] = \
+            A.indptr, A.indices, A.data, l, u
+    np.savez_compressed(os.path.join(dest, "ref_drone_S12.npz"), **out)
+
 
 def _car_model(m, M, method, alpha, seed=0):
     """Model(M, method, alpha) of car/driving.py:83-120 (draws from the global legacy RNG)."""

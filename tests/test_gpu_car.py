@@ -216,3 +216,35 @@ def test_nonfinite_guard_counts_coincident_pedestrians():
     bad.get_constraints_coeffs(us, 1)
     with pytest.raises(SaaError):
         bad.path.check_finite()
+
+
+@pytest.mark.parametrize("S", [4, 12, 31])
+@pytest.mark.parametrize("method", ["saa", "baseline"])
+def test_other_horizons_run_the_generic_kernels(S, method):
+    """driving_params.S is a module constant in the reference (car/driving_params.py:11); a horizon other
+    than 20 runs the generic kernel (csrc/generic_kernels.cuh).  Driven through DevicePath."""
+    from oracle.oracle_b import CarOracleB
+    from riskaversetrajopt_b200 import _lib
+    from riskaversetrajopt_b200.car import driving_params as cp
+    from riskaversetrajopt_b200.car.driving import BETA
+    from riskaversetrajopt_b200.device_path import DevicePath
+    M = 41
+    rs = np.random.RandomState(S)
+    x0 = np.repeat(np.asarray(cp.state_init, dtype=np.float64)[None, :], M, axis=0)
+    x0[:, 4:] += rs.randn(M, 4) * np.array([0.1, 0.1, 1e-2, 1e-2])
+    ws, wr = rs.uniform(0.025, 0.175, M), rs.uniform(0.005, 0.095, M)
+    DWs = np.sqrt(cp.dt) * rs.randn(M, S, 8)
+    if method == 'baseline':
+        DWs, ws, wr = 0 * DWs, 0 * ws, 0 * wr
+    p = DevicePath(_lib.SAA_CAR, method, S, 0.05, M)
+    p.set_params_car(cp, BETA, cp.OSQP_TOL)
+    p.set_samples_car(x0, ws, wr, DWs)
+    ref = CarOracleB(x0, ws, wr, DWs, method, 0.05)
+    us = 0.01 + 0.3 * rs.randn(S, 2)
+    for it in (0, 1, 3):
+        _check(*p.csc(us, it), *ref.get_constraints_coeffs(us, it))
+    assert np.allclose(p.rollout(us).cpu().numpy(), ref.rollout(us), rtol=1e-11, atol=1e-12)
+    Z, out3 = p.cvar_terms(us, t_risk=-1.0)
+    Zr = ref.monte_carlo_constraints(us)[1]
+    assert np.allclose(Z.cpu().numpy(), Zr, rtol=1e-10, atol=1e-12)
+    assert np.isclose(out3[0].item(), np.maximum(Zr + 1.0, 0).sum(), rtol=1e-10)

@@ -249,12 +249,14 @@ def test_monte_carlo_statistics_on_device(drone_seed0):
     Zh = Z.cpu().numpy()
     for alpha in (0.05, 0.1, 0.3):
         xth = int(np.floor(alpha * M))
-        assert mc.monte_carlo_var(Z, alpha) == np.sort(Zh)[M - xth - 1]        # drone_main_plot.py:649-651
+        assert mc.monte_carlo_var(model.path, Z, alpha) == np.sort(Zh)[M - xth - 1]        # drone_main_plot.py:649-651
         # the LP of drone_risk.py:664-695 minimises t + mean((Z-t)^+)/alpha over t: brute force on a grid of
         # order statistics
         cand = np.sort(Zh)[M - xth - 50:M - xth + 50]
         obj = np.array([t + np.maximum(Zh - t, 0).mean() / alpha for t in cand])
-        assert np.isclose(mc.monte_carlo_avar(Z, alpha), obj.min(), rtol=1e-9, atol=1e-12)
+        assert np.isclose(mc.monte_carlo_avar(model.path, Z, alpha), obj.min(), rtol=1e-9, atol=1e-12)
+        assert np.isclose(mc.monte_carlo_avar(model.path, Z, alpha, t_risk=0.1),
+                          0.1 + np.maximum(Zh - 0.1, 0).mean() / alpha, rtol=1e-12)
     assert mc.fraction_satisfied(Z) == np.mean(Zh <= 1e-6)
     assert isinstance(Z, torch.Tensor) and Z.is_cuda
 
@@ -297,3 +299,47 @@ def test_factored_record_expands_to_identical_entries(drone_seed0, M, scp_iter):
         lo = 7 + M
         assert torch.equal(u[lo:lo + 60 * M], full['u'][lo:lo + 60 * M])
     assert torch.equal(p.mean_sums, sums_full)
+
+
+@pytest.mark.parametrize("S", [3, 5, 12, 30, 32])
+@pytest.mark.parametrize("method", ["saa", "baseline"])
+def test_other_horizons_run_the_generic_kernels(S, method):
+    """The reference's Model takes S as a constructor argument (drone/drone_risk.py:70-83, dt = T / S).
+    S = 20 runs the tuned kernels, every other horizon the generic ones (csrc/generic_kernels.cuh):
+    same outputs against the oracle, including relaxed iterations, rollout and the CVaR terms."""
+    from oracle.oracle_b import DroneOracleB
+    from riskaversetrajopt_b200.drone import drone_params as dp
+    from riskaversetrajopt_b200.drone.drone_risk import Model
+    M = 37
+    rs = np.random.RandomState(S)
+    masses = rs.uniform(dp.mass_nom - dp.mass_delta, dp.mass_nom + dp.mass_delta, M)
+    obs_Qs = np.zeros((M, 3, 3, 3))
+    for o in range(3):
+        for d in range(3):
+            obs_Qs[:, o, d, d] = 1. / (dp.obs_radii[o] + rs.uniform(-dp.obs_radii_deltas, dp.obs_radii_deltas, M))**2
+    DWs = np.sqrt(dp.T / S) * rs.randn(M, S, 6)
+    model = Model(S, DWs, masses, obs_Qs, method, 0.2)
+    ref = DroneOracleB(S, DWs, masses, obs_Qs, method, 0.2)
+    us = model.initial_guess_us_mat() + 0.3 * rs.randn(S, 3)
+    for it in (0, 2, 5):
+        _check(*model.get_constraints_coeffs(us, it), *ref.get_constraints_coeffs(us, it), RTOL64)
+    assert np.allclose(model.us_to_state_trajectories(us), ref.rollout(us)[0], rtol=1e-11, atol=1e-13)
+    sat, Z = model.monte_carlo_constraints(us)
+    assert np.allclose(Z, ref.monte_carlo_constraints(us)[1], rtol=1e-10, atol=1e-12)
+    avar = model.monte_carlo_avar(us, 0.1)
+    assert np.isclose(avar, 0.1 + np.mean(np.maximum(Z - 0.1, 0)) / 0.2, rtol=1e-10)
+
+
+def test_generic_horizon_vs_reference_execution():
+    """S = 12, M = 6 through the reference's own code (tests/golden/ref_drone_S12.npz)."""
+    from riskaversetrajopt_b200.drone.drone_risk import Model
+    g = np.load(os.path.join(G, "ref_drone_S12.npz"))
+    model = Model(12, g["DWs"], g["masses"], g["obs_Qs"], 'saa', 0.1)
+    for it in (0, 2):
+        A, l, u = model.get_constraints_coeffs(g["us"], it)
+        k = f"iter{it}"
+        assert np.array_equal(A.indptr, g[k + "_indptr"]) and np.array_equal(A.indices, g[k + "_indices"])
+        assert rel_err(A.data, g[k + "_data"]) < RTOL64
+        assert np.allclose(u, g[k + "_u"], rtol=RTOL64, atol=1e-12)
+        f = np.isfinite(g[k + "_l"])
+        assert np.allclose(l[f], g[k + "_l"][f], rtol=RTOL64, atol=1e-12)

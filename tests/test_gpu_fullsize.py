@@ -154,3 +154,73 @@ def test_car_million_samples_properties():
     Zc, out3 = path.cvar_terms(us, t_risk=-1.0, sat_tol=1e-6)
     assert torch.allclose(Z - cp.OSQP_TOL, Zc, rtol=0, atol=1e-14)
     assert out3[2].item() == Zc.max().item()
+
+
+def test_drone_two_million_samples_int64_offsets():
+    """nnz = 1263 M + 180 exceeds 2^31 from M ~ 1.7e6: 64-bit CSC offsets in the kernels and an int64
+    pattern on the host.  M = 2e6 (20 GB of matrix values): sampled samples -- the first, the last
+    and those around the 2^31 element boundary of every long column -- against the oracle, at
+    positions taken from the int64 column pointers of the library."""
+    import torch
+    if torch.cuda.get_device_properties(0).total_memory < 100e9:
+        pytest.skip("needs ~45 GB of device memory")
+    sys.path.insert(0, ROOT)
+    import bench
+    from oracle.oracle_b import DroneOracleB
+    from riskaversetrajopt_b200 import _lib
+    from riskaversetrajopt_b200._lib import lib, check
+    from riskaversetrajopt_b200.device_path import DevicePath
+    from riskaversetrajopt_b200.drone import drone_params as dp
+    M = 2_000_000
+    dev = torch.device("cuda", 0)
+    DWs, masses, obs_Qs = bench.synthetic_drone_samples(M, 5, dev)
+    path = DevicePath(_lib.SAA_DRONE, 'saa', S, 0.1, M, device=0)
+    path.set_params_drone(dp, dp.OSQP_TOL)
+    path.set_samples_drone(masses, DWs, obs_Qs)
+    n_rows, n_cols, nnz = path.pattern_sizes()
+    assert nnz == 1263 * M + 180 > 2**31 and n_rows == 68 + 61 * M and n_cols == 62 + M
+    # int64 column pointers from the library (row indices not materialised: 20 GB on the host)
+    indptr = np.empty(n_cols + 1, dtype=np.int64)
+    check(lib.saa_pattern_i64(path.handle, 0, indptr.ctypes.data, None), path.handle)
+    assert indptr[0] == 0 and indptr[-1] == nnz and np.all(np.diff(indptr) > 0)
+    # the int32 entry point must refuse this size
+    i32 = np.empty(4, dtype=np.int32)
+    assert lib.saa_pattern_i32(path.handle, 0, i32.ctypes.data, i32.ctypes.data) == -1
+    for j in range(S - 1):
+        for a in range(2):
+            assert indptr[j * 3 + a] + 2 == _col(j, a, M)[0]          # 2 final rows precede the sample runs
+    assert indptr[60] == 1140 * M + 177                                # y columns start here
+    assert indptr[60 + M] - indptr[60] == 62 * M                       # M y columns of 2 + 60 entries
+    us = bench.bench_us()
+    b = path.assemble(us, 2)
+    Ax, u = b['Ax'], b['u']
+    assert Ax.numel() == nnz
+    row_s0 = 6 + 1 + M
+    # samples whose runs straddle element 2^31 in some column, plus the ends and random ones
+    idx = [0, 1, 15, 16, M - 1, M - 16, M - 17]
+    for j in range(S - 1):
+        for a in range(2):
+            start, L = _col(j, a, M)
+            if start < 2**31 < start + M * L:
+                i = (2**31 - start) // L
+                idx += [int(i) - 1, int(i), int(i) + 1]
+    assert len(idx) > 7                                                # the boundary IS crossed inside runs
+    idx = np.unique(np.clip(np.concatenate([idx, np.random.RandomState(1).randint(0, M, 24)]), 0, M - 1))
+    it = torch.as_tensor(idx, device=dev)
+    ref = DroneOracleB(S, DWs[it].cpu().numpy(), masses[it].cpu().numpy(), obs_Qs[it].cpu().numpy(), 'saa', 0.1)
+    _, _, _, g_du, g_up = ref.per_sample(us)
+    rel = lambda got, want: float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-12)))
+    ub = u[(row_s0 + it[:, None] * 60 + torch.arange(60, device=dev)[None, :])].cpu().numpy()
+    assert rel(ub, 0.01 * g_up.reshape(len(idx), -1)) < 1e-9
+    for j in range(S - 1):
+        for a in range(2):
+            start, L = _col(j, a, M)
+            pos = start + it[:, None] * L + torch.arange(L, device=dev)[None, :]
+            got = Ax[pos].cpu().numpy().reshape(len(idx), 3, L // 3)
+            want = 0.01 * g_du[:, :, j + 1:, j * 3 + a]
+            assert rel(got, want) < 1e-9, (j, a)
+    # constants beyond 2^31: t column (last) and the y columns
+    tcol = int(indptr[60 + M + 1])
+    assert Ax[tcol].item() == M * 0.1 and bool((Ax[tcol + 1:tcol + 1 + 1000] == -0.01).all())
+    ycol = int(indptr[60 + M - 1])
+    assert Ax[ycol].item() == 1.0 and Ax[ycol + 1].item() == -1.0 and bool((Ax[ycol + 2:ycol + 62] == -0.01).all())
