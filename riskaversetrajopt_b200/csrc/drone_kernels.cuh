@@ -135,13 +135,72 @@ __device__ __forceinline__ void drone_flush(T *base, T *stg, i64 g0x, i64 g0y, i
 #endif
 }
 
+#ifndef SAA_LINE_OWN
+#define SAA_LINE_OWN 0     // 1: every 128-byte line of a column is written whole by ONE warp (see drone_flush_own)
+#endif
+
+// What a warp knows about its neighbours in the block (consecutive tiles = adjacent runs)
+template <typename T> struct DroneNbr {
+  const T *next;      // staging buffer of warp + 1 (nullptr: no next tile in this block)
+  int ns_next;        // its valid samples
+  bool has_prev;      // warp - 1 holds the preceding tile
+};
+
+// Line-ownership copy-out.  The runs of consecutive tiles are adjacent in the column but start at
+// an arbitrary 8-byte phase, so every run shares its first and last 128-byte line with a
+// neighbour; a line written in two pieces by two warps costs ~3.4 full-line writes
+// (profiles/README.md, tools/wbw3.cu).  Here the warps of a block move through the columns in
+// lockstep (two block barriers per column pair): once all have staged, a warp writes its own run
+// from the first line boundary on AND completes its last line with the head elements it reads from
+// the next warp's staging buffer; only the two ends of the block's 96-sample run stay partial.
+template <typename T, int LEN>
+__device__ __forceinline__ void drone_flush_own(T *base, const T *stg, const DroneNbr<T> &N, i64 g0x, i64 g0y,
+                                                int ns, int lane) {
+  using St = Stager<T, LEN>;
+  constexpr int VEC = St::VEC, LINE = 128 / (int)sizeof(T);
+  __syncthreads();                       // every warp of the block has staged this column pair
+  const int n = ns * LEN;
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {
+    const i64 g0 = a ? g0y : g0x;
+    const int t0 = (int)(g0 & (LINE - 1)), need0 = (LINE - t0) & (LINE - 1);
+    const int e0 = (N.has_prev && t0 != 0 && n >= need0) ? need0 : 0;      // the previous warp completes that line
+    const i64 G = g0 + n;
+    const int t1 = (int)(G & (LINE - 1)), need1 = LINE - t1;
+    const bool own_tail = N.next != nullptr && t1 != 0 && N.ns_next * LEN >= need1 && n - t1 >= e0;
+    const int e1 = own_tail ? n - t1 : n;
+    St::copy_range(base, stg, a, g0, e0, e1, lane);
+    if (own_tail && lane < LINE / VEC) {
+      const int off = (int)(g0 & (VEC - 1)), offn = (int)(G & (VEC - 1));
+      T tmp[VEC];
+#pragma unroll
+      for (int q = 0; q < VEC; ++q) {
+        const int ge = lane * VEC + q;                                       // position inside the line
+        tmp[q] = ge < t1 ? *St::elem(stg, a, n - t1 + ge, off) : *St::elem(N.next, a, ge - t1, offn);
+      }
+      __stcs(reinterpret_cast<int4 *>(base + (G - t1) + lane * VEC), *reinterpret_cast<const int4 *>(tmp));
+    }
+  }
+  __syncthreads();                       // the staging buffers may be overwritten
+}
+
+// barriers of drone_flush_own for a warp of the block that has no tile in this round
+template <int S, int J>
+__device__ __forceinline__ void drone_idle_barriers() {
+  if constexpr (J < S - 1) {
+    __syncthreads();
+    __syncthreads();
+    drone_idle_barriers<S, J + 1>();
+  }
+}
+
 // ---- sensitivity chains, one CSC column pair (x and y column of control step J) per pass ----
 template <typename T, typename TO, int S, int J, int MODE>
 __device__ __forceinline__ void drone_chains(const DroneArgs<T, TO, S> &A, const DroneOut<TO> &O,
                                              const T (&P)[S + 1], const T (&A22)[S],
                                              const T (&q2)[3], const T (&oca)[3], T a21, T dtm,
                                              TO *stage, double *wacc, int a, int si, int lane, i64 s0,
-                                             int ns, bool active) {
+                                             int ns, bool active, const DroneNbr<TO> &N) {
   using Rd = DroneRed<S>;
   if constexpr (J >= S - 1) {
     // last control step: no sample rows, only d v_S/du = dt/m enters the mean rows
@@ -204,9 +263,13 @@ __device__ __forceinline__ void drone_chains(const DroneArgs<T, TO, S> &A, const
       if (si == 0) { wacc[Rd::FIN_P + a * (S - 1) + J] += rp; wacc[Rd::FIN_V + a * S + J] += rv; }
     }
     if constexpr (MODE == DRONE_FACTOR) drone_flush<TO, SLEN>(O.fsp, stg, f0x, f0y, a, si, ns, lane);
+#if SAA_LINE_OWN && SAA_COPY != 3
+    else drone_flush_own<TO, SLEN>(O.Ax, stg, N, g0x, g0y, ns, lane);
+#else
     else drone_flush<TO, SLEN>(O.Ax, stg, g0x, g0y, a, si, ns, lane);
+#endif
     drone_chains<T, TO, S, J + 1, MODE>(A, O, P, A22, q2, oca, a21, dtm, stage, wacc, a, si, lane, s0, ns,
-                                    active);
+                                    active, N);
   }
 }
 
@@ -237,11 +300,29 @@ drone_assemble_kernel(const __grid_constant__ DroneArgs<T, TO, S> A) {
   TO *const ub_ptr = (TO *)ub_base;
   const i64 ntiles = (A.M + kTileSamples - 1) / kTileSamples;
   const i64 tstride = (i64)gridDim.x * WARPS;
+#if SAA_LINE_OWN && SAA_COPY != 3
+  constexpr bool kOwn = MODE != DRONE_FACTOR;        // lockstep blocks: every warp runs every round
+#else
+  constexpr bool kOwn = false;
+#endif
 #pragma unroll 1
-  for (i64 tile = (i64)blockIdx.x * WARPS + warp; tile < ntiles; tile += tstride) {
+  for (i64 tile0 = (i64)blockIdx.x * WARPS; tile0 < ntiles; tile0 += tstride) {
+    const i64 tile = tile0 + warp;
+    if (tile >= ntiles) {
+      if constexpr (kOwn) { drone_idle_barriers<S, 0>(); continue; }
+      else break;
+    }
     const i64 s0 = tile * kTileSamples;
     const int ns = (int)min((i64)kTileSamples, A.M - s0);
     const bool active = si < ns;
+    DroneNbr<TO> N{nullptr, 0, false};
+    if constexpr (kOwn) {
+      N.has_prev = warp > 0;
+      if (warp + 1 < WARPS && tile + 1 < ntiles) {
+        N.next = sm.stage[warp + 1];
+        N.ns_next = (int)min((i64)kTileSamples, A.M - (s0 + kTileSamples));
+      }
+    }
     const i64 s = s0 + (active ? si : 0);
     T P[S + 1], A22[S];
     T q2[3], oca[3];
@@ -340,7 +421,7 @@ drone_assemble_kernel(const __grid_constant__ DroneArgs<T, TO, S> A) {
     }
 
     // ---------------- sensitivity chains, one CSC column pair per control step -
-    drone_chains<T, TO, S, 0, MODE>(A, O, P, A22, q2, oca, a21, dtm, stage, wacc, a, si, lane, s0, ns, active);
+    drone_chains<T, TO, S, 0, MODE>(A, O, P, A22, q2, oca, a21, dtm, stage, wacc, a, si, lane, s0, ns, active, N);
   }
 
 #if SAA_COPY == 3

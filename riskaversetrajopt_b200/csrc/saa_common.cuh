@@ -188,6 +188,52 @@ template <typename T, int LEN> struct Stager {
     bulk_commit();
   }
 
+  // ---- line-ownership copy-out (SAA_LINE_OWN) -------------------------------------------------
+  // element e of column a's staged run; off = (global start of the run) & (VEC-1)
+  __device__ __forceinline__ static const T *elem(const T *stage, int a, int e, int off) {
+    if (ROWWISE) {
+      constexpr unsigned MAGIC = (unsigned)((0x100000000ull + LEN - 1) / LEN);
+      const int row = (int)__umulhi((unsigned)e, MAGIC);
+      return stage + (a * kTileSamples + row) * RSTRIDE + off + (e - row * LEN);
+    }
+    return stage + a * YBASE + off + e;
+  }
+  // Copy elements [e0, e1) of column a's run to base + g0 + e with 16-byte stores on 16-byte
+  // aligned global addresses (scalars for the < VEC unaligned elements at either end).
+  __device__ __forceinline__ static void copy_range(T *base, const T *stage, int a, i64 g0, int e0, int e1,
+                                                    int lane) {
+    if (e1 <= e0) return;
+    const int off = (int)(g0 & (VEC - 1));
+    const int h = min(e1 - e0, (int)((VEC - ((g0 + e0) & (VEC - 1))) & (VEC - 1)));
+    const int ea = e0 + h;
+    const int nvec = (e1 - ea) / VEC, tail = e1 - ea - nvec * VEC;
+    T *dst = base + g0;
+#pragma unroll 4
+    for (int v = lane; v < nvec; v += 32) {
+      const int e = ea + v * VEC;
+      int4 val;
+      if (ROWWISE) {
+        constexpr unsigned MAGIC = (unsigned)((0x100000000ull + LEN - 1) / LEN);
+        const int row = (int)__umulhi((unsigned)e, MAGIC);
+        const int idx = e - row * LEN;
+        const T *src = stage + (a * kTileSamples + row) * RSTRIDE + off + idx;
+        if (idx + VEC <= LEN) {
+          val = *reinterpret_cast<const int4 *>(src);
+        } else {                                   // the vector straddles two (padded) staging rows
+          T tmp[VEC];
+#pragma unroll
+          for (int q = 0; q < VEC; ++q) tmp[q] = *elem(stage, a, e + q, off);
+          val = *reinterpret_cast<const int4 *>(tmp);
+        }
+      } else {
+        val = *reinterpret_cast<const int4 *>(stage + a * YBASE + off + e);
+      }
+      __stcs(reinterpret_cast<int4 *>(dst + e), val);
+    }
+    if (lane < h) st_stream(dst + e0 + lane, *elem(stage, a, e0 + lane, off));
+    if (lane < tail) st_stream(dst + ea + nvec * VEC + lane, *elem(stage, a, ea + nvec * VEC + lane, off));
+  }
+
   // Warp-cooperative copy of column a's staged run with 16-byte shared loads and 16-byte
   // streaming global stores (consecutive lanes -> consecutive 16-byte chunks); the (< VEC)
   // unaligned head / tail elements of a run or row go out as scalar stores.

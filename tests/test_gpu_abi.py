@@ -13,8 +13,9 @@ def test_create_rejects_bad_arguments(built_lib):
     h = C.c_void_p()
     assert lib.saa_create(C.byref(h), 7, 0, 0, 10, 10, 0, 20, 0.1, 64, 0) == -1          # unknown problem
     assert b"problem" in lib.saa_last_error(None)
-    assert lib.saa_create(C.byref(h), 0, 0, 0, 10, 10, 0, 19, 0.1, 64, 0) == -1          # S not instantiated
-    assert b"S = 20" in lib.saa_last_error(None)
+    assert lib.saa_create(C.byref(h), 0, 0, 0, 10, 10, 0, 33, 0.1, 64, 0) == -1          # horizon out of range
+    assert b"S <= 32" in lib.saa_last_error(None)
+    assert lib.saa_create(C.byref(h), 0, 0, 0, 10, 10, 0, 2, 0.1, 64, 0) == -1
     assert lib.saa_create(C.byref(h), 0, 0, 0, 10, 5, 0, 20, 0.1, 64, 0) == -1           # M_local > M_global
     assert lib.saa_create(C.byref(h), 0, 0, 0, 10, 10, 0, 20, 0.1, 16, 0) == -1          # precision
     assert lib.saa_create(C.byref(h), 0, 0, 0, 10, 10, 0, 20, 0.1, 64, 99) == -1         # device index
