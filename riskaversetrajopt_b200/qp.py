@@ -25,6 +25,19 @@ import scipy.sparse.linalg as spla
 _INF = 1e20
 
 
+def _bounds(l, u):
+    """Bounds as the solver uses them.  NaN bounds (the reference's car problem at scp_iter 0 has
+    ``-inf * 0 = nan`` lower bounds on rows whose entries were zeroed, car/driving.py:411-415; OSQP
+    rejects NaN) are treated as "no bound": the rows are empty, so any finite value is equivalent."""
+    l = np.asarray(l, dtype=np.float64) if l is not None else None
+    u = np.asarray(u, dtype=np.float64) if u is not None else None
+    if l is not None:
+        l = np.maximum(np.where(np.isnan(l), -_INF, l), -_INF)
+    if u is not None:
+        u = np.minimum(np.where(np.isnan(u), _INF, u), _INF)
+    return l, u
+
+
 def make_solver(name=None):
     name = name or 'admm'
     if name == 'osqp':
@@ -48,12 +61,13 @@ class OSQPLike:
         self.P = sp.triu(self.P, format='csc') + sp.triu(self.P, 1, format='csc').T   # symmetric
         self.A = sp.csc_matrix(A, dtype=np.float64).copy()
         self.q = np.asarray(q, dtype=np.float64).copy()
-        self.l = np.maximum(np.asarray(l, dtype=np.float64), -_INF)
-        self.u = np.minimum(np.asarray(u, dtype=np.float64), _INF)
+        self.l, self.u = _bounds(l, u)
         if polish:
             # OSQP's polishing step returns a high-accuracy solution of the active-set KKT system;
-            # this stand-in emulates it by iterating to 1e-6 (the SCP of the reference does not
-            # converge when its QPs are only solved to 3e-4, see examples/car_scp.py)
+            # this stand-in has no polishing: ``polish=True`` is EMULATED by iterating to 1e-6 with a
+            # larger iteration cap (the SCP of the reference does not converge when its QPs are only
+            # solved to 3e-4, see examples/car_scp.py).  There are no infeasibility certificates: an
+            # infeasible QP runs to ``max_iter`` and reports 'maximum iterations reached'.
             eps_abs, eps_rel, max_iter = min(eps_abs, 1e-6), min(eps_rel, 1e-6), max(max_iter, 200000)
         self.opts = SimpleNamespace(eps_abs=eps_abs, eps_rel=eps_rel, max_iter=max_iter, rho=rho,
                                     sigma=sigma, alpha=alpha, warm_start=warm_start, verbose=verbose,
@@ -120,9 +134,9 @@ class OSQPLike:
             self.q = np.asarray(q, dtype=np.float64).copy()
             self.qs = self.c * self.D * self.q
         if l is not None:
-            self.l = np.maximum(np.asarray(l, dtype=np.float64), -_INF)
+            self.l = _bounds(l, None)[0]
         if u is not None:
-            self.u = np.minimum(np.asarray(u, dtype=np.float64), _INF)
+            self.u = _bounds(None, u)[1]
         if l is not None or u is not None:
             eq_before = np.abs(self.us - self.ls) < 1e-10
             self.ls, self.us = self.E * self.l, self.E * self.u
