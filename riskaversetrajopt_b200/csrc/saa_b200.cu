@@ -2,12 +2,14 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 
 #include "saa_common.cuh"
 #include "layout.cuh"
 #include "drone_kernels.cuh"
+#include "drone32_kernels.cuh"
 #include "car_kernels.cuh"
 #include "hopper_kernels.cuh"
 #include "tail_kernels.cuh"
@@ -24,6 +26,13 @@ constexpr int kS = 20;            // horizon the kernels are instantiated for (r
 #endif
 constexpr int kWarps = SAA_WARPS;    // warps per block of the assemble kernels
 constexpr int kBlocksPerSM = SAA_BPS; // resident blocks per SM (persistent grid = SMs x this)
+#ifndef SAA_DRONE_TILE_DEFAULT
+#define SAA_DRONE_TILE_DEFAULT 16
+#endif
+#ifndef SAA_WARPS32
+#define SAA_WARPS32 7
+#endif
+constexpr int kWarps32 = SAA_WARPS32; // warps per block of the 32-sample-tile drone kernel (one block per SM)
 
 thread_local std::string g_create_error;
 
@@ -46,6 +55,7 @@ struct saa_handle {
   // scratch
   int n_sms = kSMs;
   int reserve_sms = 0;         // SMs the persistent assemble grids leave free (saa_reserve_sms)
+  int drone_tile = SAA_DRONE_TILE_DEFAULT;   // samples per warp tile of the drone assemble kernel: 16 | 32 (env SAA_DRONE_TILE)
   double *d_partials = nullptr; i64 partials_len = 0;
   double *d_sums = nullptr;
   double *d_means_scratch = nullptr; i64 means_scratch_len = 0;   // saa_linearize_means (may run on a side stream)
@@ -301,8 +311,9 @@ int launch_drone_assemble(saa_handle *h, const double *us, int scp_iter, void *A
   A.ub = relaxed ? nullptr : (TO *)u;         // relaxed: bounds are the constant +-bound
   A.ub_off = L.row_s0 + h->first_out * L.R;
   A.Z = (TO *)Z;
-  const i64 ntiles = (A.M + kTileSamples - 1) / kTileSamples;
-  const int grid = grid_for(h, ntiles, kWarps, kBlocksPerSM);
+  const bool tile32 = MODE == DRONE_FULL && h->drone_tile == 32;
+  const i64 ntiles = tile32 ? (A.M + kTile32 - 1) / kTile32 : (A.M + kTileSamples - 1) / kTileSamples;
+  const int grid = tile32 ? grid_for(h, ntiles, kWarps32, 1) : grid_for(h, ntiles, kWarps, kBlocksPerSM);
   // rows [0, grid) of the partial sums come from the assemble kernel, rows [grid, grid + gridz)
   // from the z-axis kernel
   constexpr int kZWarps = 4;
@@ -311,9 +322,17 @@ int launch_drone_assemble(saa_handle *h, const double *us, int scp_iter, void *A
   int rc = ensure_scratch(h, (i64)(grid + gridz) * DroneRed<kS>::N);
   if (rc) return rc;
   A.partials = h->d_partials;
-  auto kern = drone_assemble_kernel<T, TO, kS, kWarps, MODE>;
-  SAA_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
-  kern<<<grid, kWarps * 32, sizeof(Smem), st>>>(A);
+  if (tile32) {
+    using Smem32 = Drone32Smem<TO, kS, kWarps32>;
+    static_assert(sizeof(Smem32) <= 232448, "drone32: shared memory over the per-block limit");
+    auto kern32 = drone_assemble32_kernel<T, TO, kS, kWarps32>;
+    SAA_CUDA(h, cudaFuncSetAttribute(kern32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem32)));
+    kern32<<<grid, kWarps32 * 32, sizeof(Smem32), st>>>(A);
+  } else {
+    auto kern = drone_assemble_kernel<T, TO, kS, kWarps, MODE>;
+    SAA_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+    kern<<<grid, kWarps * 32, sizeof(Smem), st>>>(A);
+  }
   SAA_CUDA(h, cudaGetLastError());
   if (MODE == DRONE_EXPAND) return SAA_OK;
   drone_axis_mean_kernel<T, TO, kS, kZWarps><<<gridz, kZWarps * 32, 0, st>>>(A, 2, h->d_partials + (i64)grid * DroneRed<kS>::N);
@@ -501,6 +520,7 @@ int saa_create(saa_handle **out, int problem, int method, int variant, int64_t M
   h->M_local = M_local; h->M_global = M_global; h->sample_offset = sample_offset; h->alpha = alpha;
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->n_sms = prop.multiProcessorCount;
+  if (const char *e = std::getenv("SAA_DRONE_TILE")) h->drone_tile = std::atoi(e) == 32 ? 32 : 16;
   if (problem != SAA_HOPPER) {
     int rc = set_geometry(h, M_global, sample_offset);
     if (rc) { g_create_error = h->err; delete h; return rc; }

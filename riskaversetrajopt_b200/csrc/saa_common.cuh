@@ -144,7 +144,7 @@ __device__ __forceinline__ void fence_async_smem() {
 // A run that starts at global element g0 is staged at offset (g0 mod VEC) so that
 // 16-byte aligned global addresses map to 16-byte aligned shared addresses; the
 // (< VEC) head / tail elements go out as plain stores.
-template <typename T, int LEN> struct Stager {
+template <typename T, int LEN, int ROWS = kTileSamples> struct Stager {
   static constexpr int VEC = 16 / (int)sizeof(T);
 #ifdef SAA_TMA_DENSE_ONLY
   static constexpr bool ROWWISE = false;
@@ -152,12 +152,12 @@ template <typename T, int LEN> struct Stager {
   static constexpr bool ROWWISE = (LEN % (2 * VEC) == 0);
 #endif
   static constexpr int RSTRIDE = LEN + VEC;
-  static constexpr int YBASE = ((kTileSamples * LEN + VEC - 1) / VEC + 1) * VEC;
-  static constexpr int SIZE = ROWWISE ? 2 * kTileSamples * RSTRIDE : 2 * YBASE;
+  static constexpr int YBASE = ((ROWS * LEN + VEC - 1) / VEC + 1) * VEC;
+  static constexpr int SIZE = ROWWISE ? 2 * ROWS * RSTRIDE : 2 * YBASE;
 
   __device__ __forceinline__ static T *mine(T *stage, int a, int si, i64 g0) {
     const int off = (int)(g0 & (VEC - 1));
-    return ROWWISE ? stage + (a * kTileSamples + si) * RSTRIDE + off
+    return ROWWISE ? stage + (a * ROWS + si) * RSTRIDE + off
                    : stage + a * YBASE + off + si * LEN;
   }
   // call after fence_async_smem() + __syncwarp(); g0 = global element index (in `base`) of the
@@ -167,7 +167,7 @@ template <typename T, int LEN> struct Stager {
     const int head = (VEC - off) & (VEC - 1);
     if (ROWWISE) {
       if (si < ns) {
-        T *row = stage + (a * kTileSamples + si) * RSTRIDE + off;
+        T *row = stage + (a * ROWS + si) * RSTRIDE + off;
         T *dst = base + g0 + (i64)si * LEN;
         constexpr int dummy = 0; (void)dummy;
         const int bulk = ((LEN - head) / VEC) * VEC, tail = LEN - head - bulk;
@@ -194,7 +194,7 @@ template <typename T, int LEN> struct Stager {
     if (ROWWISE) {
       constexpr unsigned MAGIC = (unsigned)((0x100000000ull + LEN - 1) / LEN);
       const int row = (int)__umulhi((unsigned)e, MAGIC);
-      return stage + (a * kTileSamples + row) * RSTRIDE + off + (e - row * LEN);
+      return stage + (a * ROWS + row) * RSTRIDE + off + (e - row * LEN);
     }
     return stage + a * YBASE + off + e;
   }
@@ -216,7 +216,7 @@ template <typename T, int LEN> struct Stager {
         constexpr unsigned MAGIC = (unsigned)((0x100000000ull + LEN - 1) / LEN);
         const int row = (int)__umulhi((unsigned)e, MAGIC);
         const int idx = e - row * LEN;
-        const T *src = stage + (a * kTileSamples + row) * RSTRIDE + off + idx;
+        const T *src = stage + (a * ROWS + row) * RSTRIDE + off + idx;
         if (idx + VEC <= LEN) {
           val = *reinterpret_cast<const int4 *>(src);
         } else {                                   // the vector straddles two (padded) staging rows
@@ -246,7 +246,7 @@ template <typename T, int LEN> struct Stager {
       constexpr int NVMAX = LEN / VEC > 0 ? LEN / VEC : 1;   // vectors per row when off == 0
       const int nv = (LEN - head) / VEC;                     // LEN % VEC == 0: nv = NVMAX or NVMAX - 1
       const int tail = LEN - head - nv * VEC;
-      const T *src0 = stage + a * kTileSamples * RSTRIDE + off + head;
+      const T *src0 = stage + a * ROWS * RSTRIDE + off + head;
       T *dst0 = base + g0 + head;
       const int total = ns * nv;
       constexpr unsigned MAGIC0 = (unsigned)((0x100000000ull + NVMAX - 1) / NVMAX);
@@ -264,7 +264,7 @@ template <typename T, int LEN> struct Stager {
 #endif
       }
       if (lane < ns) {
-        const T *row = stage + (a * kTileSamples + lane) * RSTRIDE + off;
+        const T *row = stage + (a * ROWS + lane) * RSTRIDE + off;
         T *dst = base + g0 + (i64)lane * LEN;
         for (int e = 0; e < head; ++e) st_stream(dst + e, row[e]);
         for (int e = 0; e < tail; ++e) st_stream(dst + head + nv * VEC + e, row[head + nv * VEC + e]);

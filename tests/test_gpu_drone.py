@@ -298,7 +298,8 @@ def test_factored_record_expands_to_identical_entries(drone_seed0, M, scp_iter):
     if scp_iter >= 2:
         lo = 7 + M
         assert torch.equal(u[lo:lo + 60 * M], full['u'][lo:lo + 60 * M])
-    assert torch.equal(p.mean_sums, sums_full)
+    # same samples, same per-sample values; the reduction tree may differ between the kernels
+    assert torch.allclose(p.mean_sums, sums_full, rtol=1e-12, atol=1e-12)
 
 
 @pytest.mark.parametrize("S", [3, 5, 12, 30, 32])
