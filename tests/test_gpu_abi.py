@@ -47,7 +47,7 @@ def test_python_shim_raises(drone_seed0):
     from riskaversetrajopt_b200.drone.drone_risk import Model
     DWs, masses, obs_Qs = (x[:5] for x in drone_seed0)
     with pytest.raises(SaaError):
-        Model(19, DWs[:, :19], masses, obs_Qs)                                           # unsupported horizon
+        Model(40, np.zeros((5, 40, 6)), masses, obs_Qs)                                  # horizon beyond the generic kernels' range
     m = Model(dp.S, DWs, masses, obs_Qs)
     with pytest.raises(ValueError):
         m.get_constraints_coeffs(np.zeros((20, 2)), 2)                                   # wrong us shape
