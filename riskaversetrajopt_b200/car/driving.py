@@ -110,8 +110,25 @@ class Model:
         return A[:nrow].toarray(), l[:nrow], u[:nrow]
 
     # -- SCP glue (reference :423-456) ---------------------------------------------------
-    def define_problem(self, us_mat_p, scp_iter=0, verbose=False, solver=None):
+    def define_problem(self, us_mat_p, scp_iter=0, verbose=False, solver=None, tail=None):
+        """``tail`` as in the drone ``Model.define_problem``: None = automatic (tail-reduced subproblem from
+        scp_iter >= 1 on when M > 20 000), False = the full problem as the reference, True / margin = tail."""
         from ..qp import make_solver
+        from .. import tail_scp
+        if tail is None:
+            tail = self.method == 'saa' and self.M > tail_scp.DEFAULT_TAIL_THRESHOLD
+        if tail is not False and tail is not None and self.method == 'saa' and scp_iter >= 1:
+            if scp_iter == 1 or getattr(self, '_tail', None) is None:
+                opts = dict(tail) if isinstance(tail, dict) else {}
+                margin = opts.get('margin', 0.25) if (tail is True or isinstance(tail, dict)) else float(tail)
+                self._tail = tail_scp.TailSCP(self, n_u * S, OSQP_TOL, OSQP_POLISH, margin, solver, verbose,
+                                               max_resolves=opts.get('max_resolves', 0))
+                self._tail.define(us_mat_p, scp_iter)
+            else:
+                self._tail.update(us_mat_p, scp_iter)
+            self.osqp_prob = self._tail.prob
+            return True
+        self._tail = None
         self.P, self.q = self.get_objective_coeffs()
         self.A, self.l, self.u = self.get_constraints_coeffs(us_mat_p, scp_iter)
         if scp_iter == 0 or scp_iter == 1:
@@ -127,6 +144,12 @@ class Model:
         return True
 
     def solve(self, verbose=False):
+        if getattr(self, '_tail', None) is not None:
+            self.res, self.left_out_margin = self._tail.solve()
+            self.osqp_prob = self._tail.prob
+            if self.res.info.status != 'solved':
+                print("[solve]: Problem infeasible.")
+            return self.convert_us_vec_to_us_mat(self.res.x[:(n_u * S)]), self.res.x[-1]
         self.res = self.osqp_prob.solve()
         if self.res.info.status != 'solved':
             print("[solve]: Problem infeasible.")

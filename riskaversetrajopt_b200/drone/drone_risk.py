@@ -106,9 +106,25 @@ class Model:
         return A[:nrow].toarray(), l[:nrow], u[:nrow]
 
     # -- SCP glue (reference drone_risk.py:425-469), host solver = OSQP stand-in -----
-    def define_problem(self, us_mat_p, verbose=False, solver=None):
+    def define_problem(self, us_mat_p, verbose=False, solver=None, tail=None):
+        """``tail``: None = automatic (the tail-reduced subproblem when M > 20 000, where no host QP
+        ingests the full matrix), False = always the full problem as the reference, True / a margin
+        (float) / dict(margin=, max_resolves=) = the tail-reduced subproblem (``tail_scp``); ``self.left_out_margin``
+        reports after each solve whether the reduction was exact (<= 0)."""
         from ..qp import make_solver
+        from .. import tail_scp
         scp_iter = 2
+        if tail is None:
+            tail = self.method == 'saa' and self.M > tail_scp.DEFAULT_TAIL_THRESHOLD
+        self._tail = None
+        if tail is not False and tail is not None and self.method == 'saa':
+            opts = dict(tail) if isinstance(tail, dict) else {}
+            margin = opts.get('margin', 0.25) if (tail is True or isinstance(tail, dict)) else float(tail)
+            self._tail = tail_scp.TailSCP(self, n_u * self.S, OSQP_TOL, OSQP_POLISH, margin, solver, verbose,
+                                               max_resolves=opts.get('max_resolves', 0))
+            self._tail.define(us_mat_p, scp_iter)
+            self.osqp_prob = self._tail.prob
+            return True
         self.P, self.q = self.get_objective_coeffs()
         self.A, self.l, self.u = self.get_constraints_coeffs(us_mat_p, scp_iter)
         self.osqp_prob = make_solver(solver)
@@ -118,6 +134,9 @@ class Model:
         return True
 
     def update_problem(self, us_mat_p, scp_iter=0, verbose=False):
+        if getattr(self, '_tail', None) is not None:
+            self._tail.update(us_mat_p, scp_iter)
+            return True
         # the reference also rebuilds P, q here (:445) although they never change
         self.A, self.l, self.u = self.get_constraints_coeffs(us_mat_p, scp_iter)
         self.osqp_prob.update(l=self.l, u=self.u)
@@ -125,6 +144,12 @@ class Model:
         return True
 
     def solve(self, verbose=True):
+        if getattr(self, '_tail', None) is not None:
+            self.res, self.left_out_margin = self._tail.solve()
+            self.osqp_prob = self._tail.prob
+            if self.res.info.status != 'solved':
+                print("[solve]: Problem infeasible.")
+            return self.convert_us_vec_to_us_mat(self.res.x[:(n_u * self.S)]), self.res.x[-1]
         self.res = self.osqp_prob.solve()
         if self.res.info.status != 'solved':
             print("[solve]: Problem infeasible.")

@@ -69,3 +69,28 @@ def test_car_scp_glue_runs():
         us, t_risk = model.solve()
         us_prev = us
     assert us.shape == (20, 2) and np.all(np.isfinite(us))
+
+
+def test_tail_subproblem_as_the_update_problem_path():
+    """Model.define_problem(..., tail=...) feeds the host QP the tail-reduced subproblem; at convergence the
+    left-out margin is <= 0 (the reduction is exact there) and the SCP reaches the full problem's fixed
+    point.  With max_resolves > 0 a positive margin doubles K and re-solves at the same iterate."""
+    from riskaversetrajopt_b200.drone import drone_params as dp
+    from riskaversetrajopt_b200.drone.drone_risk import Model
+    from riskaversetrajopt_b200.drone.drone_utils import sample_uncertain_parameters
+    np.random.seed(0)
+    DWs, masses, obs_Qs = sample_uncertain_parameters('saa', M=120)
+    full, red = (Model(dp.S, DWs, masses, obs_Qs, 'saa', 0.1) for _ in range(2))
+    us_f = us_r = full.initial_guess_us_mat()
+    full.define_problem(us_f, tail=False)
+    red.define_problem(us_r, tail=dict(margin=1.0, max_resolves=1))          # K = 2 alpha M
+    assert red._tail.tail.K == 24 and full._tail is None
+    margins = []
+    for it in range(10):
+        full.update_problem(us_f, it); us_f, t_f = full.solve(verbose=False)
+        red.update_problem(us_r, it); us_r, t_r = red.solve(verbose=False)
+        margins.append(red.left_out_margin)
+    assert margins[0] == -np.inf and margins[1] == -np.inf           # relaxed iterations: nothing to check
+    assert red._tail.resolves >= 1 and red._tail.tail.K > 24          # early iterates: every sample violates -> K grew
+    assert margins[-1] <= 0                                           # at convergence the reduction is exact ...
+    assert np.max(np.abs(us_r - us_f)) < 5e-3 and abs(t_r - t_f) < 5e-3   # ... same fixed point (OSQP_TOL = 1e-3)
