@@ -49,6 +49,17 @@ int launch_car_assemble(saa_handle *h, const double *us, int scp_iter, void *Ax,
   A.Z = relaxed ? nullptr : (TO *)Z;
   A.sums = sums;
   A.nonfinite = h->d_nonfinite;
+  if (!relaxed && h->car_tile == 32) {
+    // 32-sample tiles, lane = sample with both controls (car32_kernels.cuh)
+    using Smem32 = CarSmem32<T, TO, kS, SAA_CAR32_WARPS>;
+    static_assert(sizeof(Smem32) <= 232448, "car32: shared memory over the 227 KB per-block limit");
+    const i64 nt32 = (h->M_local + kCarTile32 - 1) / kCarTile32;
+    auto kern32 = car_assemble32_kernel<T, TO, kS, SAA_CAR32_WARPS>;
+    SAA_CUDA(h, cudaFuncSetAttribute(kern32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem32)));
+    kern32<<<grid_for(h, nt32, SAA_CAR32_WARPS, 1), SAA_CAR32_WARPS * 32, sizeof(Smem32), st>>>(A);
+    SAA_CUDA(h, cudaGetLastError());
+    return SAA_OK;
+  }
   const i64 ntiles = (h->M_local + kTileSamples - 1) / kTileSamples;
   const int grid = relaxed ? 1 : grid_for(h, ntiles, kCarWarps, 1);
   auto kern = car_assemble_kernel<T, TO, kS, kCarWarps>;

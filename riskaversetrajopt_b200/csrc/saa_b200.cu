@@ -11,6 +11,7 @@
 #include "drone_kernels.cuh"
 #include "drone32_kernels.cuh"
 #include "car_kernels.cuh"
+#include "car32_kernels.cuh"
 #include "hopper_kernels.cuh"
 #include "tail_kernels.cuh"
 #include "generic_kernels.cuh"
@@ -28,6 +29,9 @@ constexpr int kWarps = SAA_WARPS;    // warps per block of the assemble kernels
 constexpr int kBlocksPerSM = SAA_BPS; // resident blocks per SM (persistent grid = SMs x this)
 #ifndef SAA_DRONE_TILE_DEFAULT
 #define SAA_DRONE_TILE_DEFAULT 16
+#endif
+#ifndef SAA_CAR_TILE_DEFAULT
+#define SAA_CAR_TILE_DEFAULT 16
 #endif
 #ifndef SAA_WARPS32
 #define SAA_WARPS32 7
@@ -55,6 +59,7 @@ struct saa_handle {
   // scratch
   int n_sms = kSMs;
   int reserve_sms = 0;         // SMs the persistent assemble grids leave free (saa_reserve_sms)
+  int car_tile = SAA_CAR_TILE_DEFAULT;       // samples per warp tile of the car assemble kernel: 16 | 32 (env SAA_CAR_TILE)
   int drone_tile = SAA_DRONE_TILE_DEFAULT;   // samples per warp tile of the drone assemble kernel: 16 | 32 (env SAA_DRONE_TILE)
   double *d_partials = nullptr; i64 partials_len = 0;
   double *d_sums = nullptr;
@@ -521,6 +526,7 @@ int saa_create(saa_handle **out, int problem, int method, int variant, int64_t M
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->n_sms = prop.multiProcessorCount;
   if (const char *e = std::getenv("SAA_DRONE_TILE")) h->drone_tile = std::atoi(e) == 32 ? 32 : 16;
+  if (const char *e = std::getenv("SAA_CAR_TILE")) h->car_tile = std::atoi(e) == 32 ? 32 : 16;
   if (problem != SAA_HOPPER) {
     int rc = set_geometry(h, M_global, sample_offset);
     if (rc) { g_create_error = h->err; delete h; return rc; }

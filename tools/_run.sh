@@ -1,8 +1,3 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 --steps 20 --warmup 5 > gpurun_out/bench_r2_n8.json 2> gpurun_out/bench_n8.err; tail -5 gpurun_out/bench_n8.err; python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/bench_r2_n8.json').read().strip().splitlines()[-1])
-for k in ('value','ms_per_step','multi_gpu_parity','target_config'):
-    print(k, d.get(k))
-print('e2e', d['e2e'].get('value'), d['e2e'].get('ms_per_step'))
-print('kernel_ms', d['roofline']['kernel_ms'], d['per_step_ms'])
-PY
+echo "== car32 tests"; SAA_CAR_TILE=32 python -m pytest tests/test_gpu_car.py tests/test_gpu_tail.py -x -q 2>&1 | tail -3
+echo "== car32"; SAA_CAR_TILE=32 KB_ONLY=car python tools/kbench_all.py 2>&1 | grep "car assemble"
+echo "== car16"; KB_ONLY=car python tools/kbench_all.py 2>&1 | grep "car assemble"
