@@ -352,6 +352,31 @@ int saa_linearize_means(saa_handle *h, const double *us_host, void *Z_dev,
  * Exact and deterministic (radix select + ordered compaction).                  */
 int saa_select_tail(saa_handle *h, const void *Z_dev, int64_t K,
                     int64_t *idx_out_dev, void *stream);
+/*
+ * The same selection over a SHARDED sample set (exact global top K, not per-rank): the radix select
+ * with its 256-bin histogram exposed between the passes so that the caller can sum it over the ranks.
+ *   saa_select_begin(h, K_global)
+ *   for pass in 0 .. saa_select_passes(h)-1:
+ *       saa_select_pass_hist(h, Z, pass, hist_dev)      local histogram of this digit (256 x uint32)
+ *       all-reduce(sum) hist_dev over the ranks          (e.g. torch.distributed on an int32 tensor)
+ *       saa_select_pass_pick(h, hist_dev, pass)          every rank picks the same digit
+ *   saa_select_counts(h, Z, gt_eq_dev)                   local #{Z > threshold}, #{Z == threshold}
+ *   all-gather the counts; ties are granted in rank (= global index) order:
+ *       take_r = min(eq_r, max(0, K_global - sum_r' gt_r' - sum_{r' < r} eq_r'))
+ *   saa_select_finish(h, Z, take_r, idx_out_dev)         local indices, ascending: gt_r + take_r of them
+ * With one rank this reproduces saa_select_tail.                                                  */
+int saa_select_passes(const saa_handle *h);
+int saa_select_begin(saa_handle *h, int64_t K_global, void *stream);
+int saa_select_pass_hist(saa_handle *h, const void *Z_dev, int pass, uint32_t *hist_dev, void *stream);
+int saa_select_pass_pick(saa_handle *h, uint32_t *hist_dev, int pass, void *stream);
+int saa_select_counts(saa_handle *h, const void *Z_dev, int64_t *gt_eq_dev, void *stream);
+int saa_select_finish(saa_handle *h, const void *Z_dev, int64_t take_ties, int64_t *idx_out_dev,
+                      void *stream);
+/* A handle created for M_local samples may work on fewer: M_active <= that capacity of them, placed
+ * at samples [first_out, first_out + M_active) of a matrix with M_out samples (the number a rank
+ * contributes to a globally selected tail changes from iteration to iteration; 0 is allowed: the
+ * launches become no-ops).                                                                        */
+int saa_set_active(saa_handle *h, int64_t M_active, int64_t M_out, int64_t first_out);
 /* dst's M_local samples := samples idx_dev[0..dst.M_local) of src (packed inputs
  * are copied device to device; dst needs saa_set_params_* but no saa_set_samples_*). */
 int saa_gather_samples(saa_handle *dst, const saa_handle *src,

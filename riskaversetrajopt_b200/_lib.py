@@ -101,6 +101,13 @@ _PROTOTYPES = {
     "saa_linearize_means": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "saa_select_tail": (C.c_int, [_H, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "saa_gather_samples": (C.c_int, [_H, _H, C.c_void_p, C.c_void_p]),
+    "saa_select_passes": (C.c_int, [_H]),
+    "saa_select_begin": (C.c_int, [_H, C.c_int64, C.c_void_p]),
+    "saa_select_pass_hist": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "saa_select_pass_pick": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_void_p]),
+    "saa_select_counts": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "saa_select_finish": (C.c_int, [_H, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "saa_set_active": (C.c_int, [_H, C.c_int64, C.c_int64, C.c_int64]),
 }
 EXPORTS = tuple(_PROTOTYPES)
 

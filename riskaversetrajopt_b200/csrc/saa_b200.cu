@@ -45,6 +45,8 @@ thread_local std::string g_create_error;
 struct saa_handle {
   int problem = 0, method = 0, variant = 0, S = 0, precision = 64, device = 0;
   i64 M_local = 0, M_global = 0, sample_offset = 0;
+  i64 M_cap = 0;                     // capacity (M_local at creation); saa_set_active may lower M_local
+  double *d_select = nullptr; i64 select_len = 0;   // state / histogram / block counts of the radix select
   i64 M_out = 0, first_out = 0;
   double alpha = 0.1;
   bool params_set = false, samples_set = false;
@@ -162,9 +164,10 @@ int upload_fin_offsets(saa_handle *h) {
 int set_geometry(saa_handle *h, i64 M_out, i64 first_out) {
   if (M_out < h->M_local || first_out < 0 || first_out + h->M_local > M_out)
     return fail(h, SAA_ERR_ARG, "output geometry does not contain the local samples");
+  const bool same = M_out == h->M_out && h->d_fin_off != nullptr;      // the final-row offsets depend on M_out only
   h->M_out = M_out; h->first_out = first_out;
   h->lay.build(h->problem, h->method, h->S, M_out, false);
-  if (h->problem != SAA_HOPPER) return upload_fin_offsets(h);
+  if (h->problem != SAA_HOPPER && !same) return upload_fin_offsets(h);
   return SAA_OK;
 }
 
@@ -522,7 +525,7 @@ int saa_create(saa_handle **out, int problem, int method, int variant, int64_t M
   if (!h) return fail(nullptr, SAA_ERR_ARG, "out of host memory");
   h->problem = problem; h->method = method; h->variant = variant; h->S = S;
   h->precision = precision; h->device = device;
-  h->M_local = M_local; h->M_global = M_global; h->sample_offset = sample_offset; h->alpha = alpha;
+  h->M_local = M_local; h->M_cap = M_local; h->M_global = M_global; h->sample_offset = sample_offset; h->alpha = alpha;
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->n_sms = prop.multiProcessorCount;
   if (const char *e = std::getenv("SAA_DRONE_TILE")) h->drone_tile = std::atoi(e) == 32 ? 32 : 16;
@@ -540,7 +543,7 @@ int saa_destroy(saa_handle *h) {
   cudaSetDevice(h->device);
   cudaFree(h->d_a); cudaFree(h->d_b); cudaFree(h->d_c); cudaFree(h->d_d);
   cudaFree(h->d_partials); cudaFree(h->d_sums); cudaFree(h->d_fin_off); cudaFree(h->d_relax_scratch);
-  cudaFree(h->d_nonfinite); cudaFree(h->d_hopper_geo); cudaFree(h->d_means_scratch);
+  cudaFree(h->d_nonfinite); cudaFree(h->d_hopper_geo); cudaFree(h->d_means_scratch); cudaFree(h->d_select);
   delete h;
   return SAA_OK;
 }
@@ -656,11 +659,21 @@ int saa_set_output_geometry(saa_handle *h, int64_t M_out, int64_t first_out) {
   return set_geometry(h, M_out, first_out);
 }
 
+int saa_set_active(saa_handle *h, int64_t M_active, int64_t M_out, int64_t first_out) {
+  if (!h) return fail(h, SAA_ERR_ARG, "NULL handle");
+  if (h->problem == SAA_HOPPER) return fail(h, SAA_ERR_ARG, "not available for the hopper");
+  if (M_active < 0 || M_active > h->M_cap) return fail(h, SAA_ERR_ARG, "need 0 <= M_active <= the handle's capacity");
+  SAA_CUDA(h, cudaSetDevice(h->device));
+  h->M_local = M_active;
+  return set_geometry(h, M_out, first_out);
+}
+
 int saa_write_constants(saa_handle *h, int scp_iter, int write_shared, void *Ax, void *l, void *u,
                         void *stream) {
   if (!h || !Ax || !l || !u) return fail(h, SAA_ERR_ARG, "NULL argument");
   if (h->problem == SAA_HOPPER) return fail(h, SAA_ERR_ARG, "hopper has no QP constants");
   if (!h->params_set) return fail(h, SAA_ERR_STATE, "set params first");
+  if (h->M_local == 0 && !write_shared) return SAA_OK;
   SAA_CUDA(h, cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
   if (h->problem == SAA_CAR && scp_iter < 1)
@@ -697,6 +710,10 @@ int saa_linearize_assemble(saa_handle *h, const double *us, int scp_iter, void *
   int rc = ensure_scratch(h, 1);
   if (rc) return rc;
   double *sums = mean_sums ? mean_sums : h->d_sums;
+  if (h->M_local == 0) {                                  // saa_set_active(0): nothing to assemble on this rank
+    SAA_CUDA(h, cudaMemsetAsync(sums, 0, saa_mean_len(h) * sizeof(double), st));
+    return SAA_OK;
+  }
   if (h->S != kS) {
     // horizon-generic kernels (generic_kernels.cuh)
     if (h->problem == SAA_DRONE)
@@ -816,6 +833,10 @@ int saa_linearize_factored(saa_handle *h, const double *us, int scp_iter, void *
   int rc = ensure_scratch(h, 1);
   if (rc) return rc;
   double *sums = mean_sums ? mean_sums : h->d_sums;
+  if (h->M_local == 0) {
+    SAA_CUDA(h, cudaMemsetAsync(sums, 0, saa_mean_len(h) * sizeof(double), st));
+    return SAA_OK;
+  }
   return h->precision == 64
              ? launch_drone_assemble<double, DRONE_FACTOR>(h, us, scp_iter, nullptr, u, Z, fsp, fp, 0, 0, sums, st)
              : launch_drone_assemble<float, DRONE_FACTOR>(h, us, scp_iter, nullptr, u, Z, fsp, fp, 0, 0, sums, st);

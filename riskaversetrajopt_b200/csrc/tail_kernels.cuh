@@ -167,14 +167,14 @@ select_write_kernel(const T *__restrict__ Z, i64 n, const SelectState *__restric
   }
 }
 
-// dst[row * dst_stride + r] = src[row * src_stride + idx[min(r, K - 1)]] for r < dst_stride:
+// dst[row * dst_stride + r] = src[row * src_stride + idx[min(r, K - 1)]] for r < n_write:
 // packed sample rows of the selected samples (the padding repeats the last one, as the pack kernels do)
 template <typename T>
 __global__ void __launch_bounds__(256)
-gather_rows_kernel(const T *__restrict__ src, i64 src_stride, T *__restrict__ dst, i64 dst_stride, int nrows,
-                   const i64 *__restrict__ idx, i64 K) {
+gather_rows_kernel(const T *__restrict__ src, i64 src_stride, T *__restrict__ dst, i64 dst_stride, i64 n_write,
+                   int nrows, const i64 *__restrict__ idx, i64 K) {
   const i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= dst_stride) return;
+  if (r >= n_write) return;
   const i64 s = idx[r < K ? r : K - 1];
   for (int row = 0; row < nrows; ++row) dst[(i64)row * dst_stride + r] = src[(i64)row * src_stride + s];
 }

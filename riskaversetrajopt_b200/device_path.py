@@ -152,6 +152,14 @@ class DevicePath:
         self._host_state.clear()
         self._csc_cache.clear()
 
+    def set_active(self, M_active, M_out, first_out):
+        """Work on ``M_active`` (<= the capacity the handle was created with) samples, placed at samples
+        ``first_out ..`` of a matrix with ``M_out`` samples (``saa_set_active``)."""
+        check(lib.saa_set_active(self._h, int(M_active), int(M_out), int(first_out)), self._h)
+        if int(M_out) != self.M_out:                       # the pattern depends on M_out only
+            self._patterns.clear(); self._bufs.clear(); self._host_state.clear(); self._csc_cache.clear()
+        self.M_local, self.M_out, self.first_out = int(M_active), int(M_out), int(first_out)
+
     def pattern_sizes(self, relaxed_pattern=False):
         r, c, n = C.c_int64(), C.c_int64(), C.c_int64()
         check(lib.saa_pattern_sizes(self._h, int(relaxed_pattern), C.byref(r), C.byref(c), C.byref(n)),

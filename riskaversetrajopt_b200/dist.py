@@ -302,6 +302,37 @@ class ShardedAssembler:
         return 380 * p.M_out + 156
 
 
+def exact_global_select(path, Z, K_total, idx_out, group=None):
+    """Exact global top-``K_total`` of the sharded values ``Z`` (this rank's ``path.M_local`` of them):
+    the library's radix select with its histogram all-reduced between the passes.  Writes this rank's
+    selected local indices (ascending) to ``idx_out`` and returns the list of per-rank counts (ties at the
+    threshold go to the lower rank = lower global index, as in the single-GPU selection)."""
+    h = path.handle
+    st = path._stream()
+    hist = torch.zeros(256, dtype=torch.int32, device=path.device)
+    check(lib.saa_select_begin(h, int(K_total), st), h)
+    for p in range(int(lib.saa_select_passes(h))):
+        check(lib.saa_select_pass_hist(h, Z.data_ptr(), p, hist.data_ptr(), st), h)
+        dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
+        check(lib.saa_select_pass_pick(h, hist.data_ptr(), p, st), h)
+    cnt = torch.zeros(2, dtype=torch.int64, device=path.device)
+    check(lib.saa_select_counts(h, Z.data_ptr(), cnt.data_ptr(), st), h)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    allc = [torch.zeros_like(cnt) for _ in range(world)]
+    dist.all_gather(allc, cnt, group=group)
+    allc = torch.stack(allc).cpu().numpy()                  # the one host synchronisation of the selection
+    rem = int(K_total) - int(allc[:, 0].sum())
+    counts = []
+    for r in range(world):
+        take = int(min(allc[r, 1], max(rem, 0)))
+        rem -= take
+        counts.append(int(allc[r, 0]) + take)
+        if r == rank:
+            mine = take
+    check(lib.saa_select_finish(h, Z.data_ptr(), mine, idx_out.data_ptr(), st), h)
+    return counts
+
+
 class ShardedTailAssembler:
     """Tail-reduced subproblem of a sharded sample set, assembled on rank 0 (peer stores).
 
@@ -310,10 +341,14 @@ class ShardedTailAssembler:
     ``offset_r .. offset_r + K_r`` of a matrix for ``K_total = sum K_r`` samples; the CVaR row keeps
     ``M_global alpha t`` and the expectation rows the mean over all ``M_global`` samples."""
 
-    def __init__(self, path, margin=0.25, K_local=None, mode='peer', group=None):
+    def __init__(self, path, margin=0.25, K_local=None, mode='peer', group=None, exact=False):
         """``mode='peer'``: the ranks' kernels store the CSC entries of their selected samples into
         rank 0's arrays; ``mode='factored'`` (drone): they store the factored record (3.4 instead of
-        9.1 KB per sample cross NVLink) and rank 0 expands it, bitwise identically."""
+        9.1 KB per sample cross NVLink) and rank 0 expands it, bitwise identically.
+        ``exact=True``: the K_total samples with the largest Z_i of the WHOLE set (``exact_global_select``:
+        all-reduced radix histograms) instead of each rank's own top K_r; the number a rank contributes
+        then changes from iteration to iteration (``self.counts``), the matrix on rank 0 is the
+        single-GPU tail-reduced matrix of all samples, sample for sample."""
         from .tail import TailSubproblem
         from . import _lib
         if mode not in ('peer', 'factored'):
@@ -328,7 +363,11 @@ class ShardedTailAssembler:
         dist.all_gather_object(counts, K, group=group)
         self.counts = [int(c) for c in counts]
         self.K_total, self.offset = sum(self.counts), sum(self.counts[:self.rank])
-        self.tail = TailSubproblem(path, K=K, out_geometry=(self.K_total, self.offset))
+        self.exact = bool(exact)
+        if self.exact:
+            # any rank may hold the whole tail: capacity = min(its shard, K_total)
+            K = min(path.M_local, self.K_total)
+        self.tail = TailSubproblem(path, K=K, out_geometry=(self.K_total, self.offset if not exact else 0))
         sub = self.tail.sub
         n_rows, _, nnz = sub.pattern_sizes(False)
         npdt = np.float64 if sub.bits == 64 else np.float32
@@ -338,7 +377,7 @@ class ShardedTailAssembler:
         self.out = dict(Ax=bufs[0], l=bufs[1], u=bufs[2], const_state=None)
         if mode == 'factored':
             self.fsp, self.fp = bufs[3], bufs[4]
-        kmax = max(self.counts)                                  # all_gather wants equal sizes: pad
+        kmax = self.K_total if self.exact else max(self.counts)  # all_gather wants equal sizes: pad
         self._idx_send = torch.zeros(kmax, dtype=torch.int64, device=sub.device)
         self._idx_all = [torch.empty(kmax, dtype=torch.int64, device=sub.device) for _ in self.counts]
 
@@ -354,6 +393,8 @@ class ShardedTailAssembler:
             raise ValueError("the sharded tail gather covers scp_iter >= 1 for the car")
         nccl = dist.get_backend(self.group) == 'nccl'
         us = broadcast_controls(us_mat, 0, self.group, device=p.device if nccl else None)
+        if self.exact:
+            return self._step_exact(us, scp_iter)
         if self.mode == 'factored' and self.rank != 0:
             us = t.select(us)
             t.sub.write_constants(self.out, scp_iter, write_shared=False)
@@ -371,6 +412,38 @@ class ShardedTailAssembler:
         if self.mode == 'factored' and self.K_total > self.counts[0]:
             t.sub.expand_factored(scp_iter, self.fsp, self.fp, self.counts[0], self.K_total - self.counts[0],
                                   b['Ax'])
+        t.finalize_means(b, scp_iter)
+        return b, torch.cat([v[:c] for v, c in zip(self._idx_all, self.counts)])
+
+    def _step_exact(self, us, scp_iter):
+        p, t = self.path, self.tail
+        f, s = t.full, t.sub
+        st = f._stream()
+        usc = f._us(us)
+        check(lib.saa_linearize_means(f.handle, usc.ctypes.data, t.Z.data_ptr(), f.mean_sums.data_ptr(), st), f.handle)
+        self.counts = exact_global_select(f, t.Z, self.K_total, t.idx, self.group)
+        K_r, off = self.counts[self.rank], sum(self.counts[:self.rank])
+        t.K = K_r
+        s.set_active(K_r, self.K_total, off)
+        check(lib.saa_gather_samples(s.handle, f.handle, t.idx.data_ptr(), st), s.handle)
+        # the slice [off, off + K_r) moves from iteration to iteration: its constants are rewritten each time
+        # (the slices of all ranks tile the K_total samples, so every constant entry is covered)
+        self.out['const_state'] = None
+        if self.mode == 'factored' and self.rank != 0:
+            s.write_constants(self.out, scp_iter, write_shared=False)
+            s.linearize_factored(usc, scp_iter, self.fsp, self.fp, self.out['u'])
+        else:
+            s.assemble(usc, scp_iter, out=self.out, write_shared=(self.rank == 0), finalize=False)
+        all_reduce_sums(p.mean_sums, self.group)
+        self._idx_send[:K_r] = t.idx[:K_r] + p.sample_offset
+        dist.all_gather(self._idx_all, self._idx_send, group=self.group)
+        torch.cuda.current_stream(p.device).synchronize()
+        dist.barrier(group=self.group)
+        if self.rank != 0:
+            return None, None
+        b = self.out
+        if self.mode == 'factored' and self.K_total > self.counts[0]:
+            s.expand_factored(scp_iter, self.fsp, self.fp, self.counts[0], self.K_total - self.counts[0], b['Ax'])
         t.finalize_means(b, scp_iter)
         return b, torch.cat([v[:c] for v, c in zip(self._idx_all, self.counts)])
 
@@ -433,15 +506,28 @@ def parity_self_check(make_path, set_params, M, us, scp_iter=2, group=None, mode
     row_s0_g = n_fin + 1 + M
     res = {}
     modes = modes or (('sharded', 'sharded_peer_means', 'peer', 'nccl') + (('factored',) if single.problem == 0 else ())
-                      + ('tail',))
+                      + ('tail', 'tail_exact'))
     for mode in modes:
         err = 0.0
         if mode == 'nccl' and M % world:
             continue
-        if mode == 'tail':
+        if mode in ('tail', 'tail_exact'):
             asm = ShardedTailAssembler(make_path(first, cnt, M), margin=0.5,
-                                       mode='factored' if single.problem == 0 else 'peer', group=group)
-            b, idx = asm.step(us, scp_iter)
+                                       mode='factored' if single.problem == 0 else 'peer', group=group,
+                                       exact=(mode == 'tail_exact'))
+            for _ in range(2 if asm.exact else 1):       # twice: the active counts are set again
+                b, idx = asm.step(us, scp_iter)
+            if rank == 0 and asm.exact:
+                # the single-GPU tail-reduced matrix of ALL samples, entry for entry
+                from .tail import TailSubproblem
+                ts = TailSubproblem(single, K=asm.K_total)
+                bs = ts.assemble(us, scp_iter)
+                torch.cuda.synchronize()
+                if not torch.equal(ts.idx, idx):
+                    err = float('inf')
+                for k in ('Ax', 'l', 'u'):
+                    err = max(err, _rel_err(b[k], bs[k]))
+                del ts
             if rank == 0:
                 torch.cuda.synchronize()
                 n_rows_t, _, indptr_t, indices_t = asm.pattern()

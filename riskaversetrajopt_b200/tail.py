@@ -114,7 +114,7 @@ class TailSubproblem:
         """max over the samples NOT selected of (Z_i - t) at the iterate of the last ``assemble``:
         <= 0 means the reduction was exact there (their y_i would be 0)."""
         mask = torch.ones_like(self.Z, dtype=torch.bool)
-        mask[self.idx] = False
+        mask[self.idx[:self.K]] = False
         if not bool(mask.any()):
             return -math.inf
         return float((self.Z[mask].max() - t_risk).item())

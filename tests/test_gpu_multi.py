@@ -116,7 +116,7 @@ def test_two_ranks_reproduce_single_gpu(problem, M):
             assert np.allclose(su[:nfin], u[:nfin], rtol=1e-12, atol=1e-14)      # global means on every rank
 
 
-def _tail_worker(rank, world, initfile, M, problem, mode, out):
+def _tail_worker(rank, world, initfile, M, problem, mode, out, exact=False, skew=None):
     import torch
     import torch.distributed as dist
     from riskaversetrajopt_b200 import _lib, dist as sd
@@ -131,6 +131,16 @@ def _tail_worker(rank, world, initfile, M, problem, mode, out):
         np.random.seed(0)
         DWs, masses, obs_Qs = sample_uncertain_parameters('saa', M=M)
         us, its, alpha = 0.1 * rs.randn(20, 3), (0, 2), 0.1
+        if skew:
+            # all the worst samples on one rank: the other contributes (next to) nothing to an exact tail
+            p = DevicePath(_lib.SAA_DRONE, 'saa', 20, alpha, M, device=rank)
+            p.set_params_drone(dp, dp.OSQP_TOL); p.set_samples_drone(masses, DWs, obs_Qs)
+            Z = torch.empty(M, dtype=torch.float64, device=f'cuda:{rank}')
+            p.assemble(us, 2, Z=Z)
+            order = np.argsort(-Z.cpu().numpy(), kind='stable')
+            order = order if skew == 'first' else order[::-1].copy()
+            DWs, masses, obs_Qs = DWs[order], masses[order], obs_Qs[order]
+            p.close()
 
         def make(first, cnt):
             p = DevicePath(_lib.SAA_DRONE, 'saa', 20, alpha, cnt, M_global=M, sample_offset=first, device=rank)
@@ -151,11 +161,11 @@ def _tail_worker(rank, world, initfile, M, problem, mode, out):
             return p
     res = {}
     first, cnt = sd.shard_range(M, world, rank)
-    asm = sd.ShardedTailAssembler(make(first, cnt), margin=0.5, mode=mode)
+    asm = sd.ShardedTailAssembler(make(first, cnt), margin=0.5, mode=mode, exact=exact)
     for it in its:
         b, idx = asm.step(us if rank == 0 else np.zeros_like(us), it)
         Zloc = asm.tail.Z.cpu().numpy()
-        sel = asm.tail.idx.cpu().numpy()
+        sel = asm.tail.idx[:asm.tail.K].cpu().numpy()
         res[('local', it)] = (Zloc, sel, first)
         if rank == 0:
             res[('tail', it)] = tuple(b[k].cpu().numpy() for k in ('Ax', 'l', 'u')) + (idx.cpu().numpy(),)
@@ -172,11 +182,16 @@ def _tail_worker(rank, world, initfile, M, problem, mode, out):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("problem,M,mode", [("drone", 1000, "peer"), ("car", 600, "peer"), ("drone", 77, "peer"),
-                                             ("drone", 1000, "factored"), ("drone", 77, "factored")])
-def test_two_ranks_tail_subproblem(problem, M, mode):
-    """Stratified tail selection on 2 ranks, rows stored into rank 0's K-sample matrix over NVLink:
-    the result is the single-GPU full matrix restricted to the selected samples."""
+@pytest.mark.parametrize("problem,M,mode,exact,skew", [
+    ("drone", 1000, "peer", False, None), ("car", 600, "peer", False, None), ("drone", 77, "peer", False, None),
+    ("drone", 1000, "factored", False, None), ("drone", 77, "factored", False, None),
+    ("drone", 1000, "peer", True, None), ("car", 600, "peer", True, None), ("drone", 1000, "factored", True, None),
+    ("drone", 400, "peer", True, "first"), ("drone", 400, "peer", True, "last"),
+    ("drone", 400, "factored", True, "first"), ("drone", 400, "factored", True, "last")])
+def test_two_ranks_tail_subproblem(problem, M, mode, exact, skew):
+    """Tail selection on 2 ranks -- stratified (each rank's own top K_r) or exact (the global top K_total,
+    whatever the split; ``skew`` puts all of the tail on one rank) -- rows stored into rank 0's K-sample
+    matrix over NVLink: the result is the single-GPU full matrix restricted to the selected samples."""
     import scipy.sparse as sp
     import torch
     import torch.multiprocessing as mp
@@ -186,7 +201,7 @@ def test_two_ranks_tail_subproblem(problem, M, mode):
     mgr = mp.Manager()
     out = mgr.dict()
     with tempfile.TemporaryDirectory() as d:
-        mp.spawn(_tail_worker, args=(2, os.path.join(d, "init"), M, problem, mode, out), nprocs=2, join=True)
+        mp.spawn(_tail_worker, args=(2, os.path.join(d, "init"), M, problem, mode, out, exact, skew), nprocs=2, join=True)
     r0, r1 = out[0], out[1]
     its = (0, 2) if problem == 'drone' else (1, 2)
     R, nu, nfin = (60, 60, 6) if problem == 'drone' else (20, 40, 4)
@@ -202,6 +217,11 @@ def test_two_ranks_tail_subproblem(problem, M, mode):
             assert np.array_equal(sel, _select_ref(Zloc, len(sel)))
             parts.append(sel + first)
         assert np.array_equal(idx, np.concatenate(parts))
+        if exact:
+            Zall = np.concatenate([r0[('local', it)][0], r1[('local', it)][0]])
+            assert np.array_equal(idx, _select_ref(Zall, len(idx)))       # the global top K_total
+            if skew and it == 2:
+                assert min(len(parts[0]), len(parts[1])) == 0
         fAx, fl, fu = r0[('single', it)]
         A_full = sp.csc_matrix((fAx, findices, findptr), shape=(fr, fc))
         As, ls, us_ = _submatrix(A_full, fl, fu, idx, M, R, nu, nfin)

@@ -197,3 +197,107 @@ def test_tail_edge_sizes_and_fp32(precision):
     base = Model(dp.S, DWs, masses, obs_Qs, 'baseline', 0.1)
     with pytest.raises(ValueError):
         base.tail_subproblem()
+
+
+def _select_over_shards(paths, Zs, K_total):
+    """dist.exact_global_select with the ranks played by several handles on one GPU (the all-reduce is a
+    tensor sum, the all-gather a stack)."""
+    import torch
+    from riskaversetrajopt_b200._lib import lib, check
+    hists = [torch.zeros(256, dtype=torch.int32, device='cuda') for _ in paths]
+    for p in paths:
+        check(lib.saa_select_begin(p._h, K_total, p._stream()), p._h)
+    for ps in range(int(lib.saa_select_passes(paths[0]._h))):
+        for p, Z, h in zip(paths, Zs, hists):
+            check(lib.saa_select_pass_hist(p._h, Z.data_ptr(), ps, h.data_ptr(), p._stream()), p._h)
+        tot = torch.stack(hists).sum(0).to(torch.int32)
+        for p, h in zip(paths, hists):
+            h.copy_(tot)
+            check(lib.saa_select_pass_pick(p._h, h.data_ptr(), ps, p._stream()), p._h)
+    cnts = []
+    for p, Z in zip(paths, Zs):
+        c = torch.zeros(2, dtype=torch.int64, device='cuda')
+        check(lib.saa_select_counts(p._h, Z.data_ptr(), c.data_ptr(), p._stream()), p._h)
+        cnts.append(c.cpu().numpy())
+    rem = K_total - sum(int(c[0]) for c in cnts)
+    out = []
+    for p, Z, c in zip(paths, Zs, cnts):
+        take = int(min(c[1], max(rem, 0))); rem -= take
+        idx = torch.full((max(1, int(c[0]) + take),), -1, dtype=torch.int64, device='cuda')
+        check(lib.saa_select_finish(p._h, Z.data_ptr(), take, idx.data_ptr(), p._stream()), p._h)
+        out.append(idx[:int(c[0]) + take].cpu().numpy())
+    return out
+
+
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+def test_exact_selection_over_shards(precision):
+    """The histogram-exchanging radix select picks the global top K whatever the split of the values over
+    the shards (ties to the lower global index), and with one shard it is saa_select_tail."""
+    import torch
+    from riskaversetrajopt_b200 import _lib
+    from riskaversetrajopt_b200.device_path import DevicePath
+    rs = np.random.RandomState(1)
+    dt = torch.float64 if precision == "fp64" else torch.float32
+    for n, splits in ((1000, (1000,)), (1000, (500, 500)), (1003, (1, 1002)), (5000, (1200, 1300, 2500)), (64, (32, 32))):
+        for kind in ("generic", "ties", "skew", "equal"):
+            z = rs.randn(n)
+            if kind == "ties":
+                z = np.round(z * 2)
+            elif kind == "skew":
+                z = np.sort(z)[::-1].copy()                          # the whole tail on the first shard
+            elif kind == "equal":
+                z[:] = 0.5
+            zc = torch.as_tensor(z).to(dt).numpy()
+            bounds = np.concatenate([[0], np.cumsum(splits)])
+            paths = [DevicePath(_lib.SAA_DRONE, 'saa', 20, 0.1, c, precision=precision) for c in splits]
+            Zs = [torch.as_tensor(zc[a:b]).cuda() for a, b in zip(bounds[:-1], bounds[1:])]
+            for K in (1, n // 10, n // 2, n):
+                parts = _select_over_shards(paths, Zs, K)
+                got = np.concatenate([p + a for p, a in zip(parts, bounds[:-1])])
+                assert np.array_equal(got, _select_ref(zc, K)), (n, splits, kind, K)
+            for p in paths:
+                p.close()
+
+
+def test_active_subset_of_a_capacity_handle(drone_seed0):
+    """saa_set_active: a handle created for K samples assembles K' <= K of them at any offset of a K_out
+    matrix; K' = 0 is a no-op (the rank contributes nothing to the tail)."""
+    import torch
+    from riskaversetrajopt_b200 import _lib
+    from riskaversetrajopt_b200._lib import lib, check
+    from riskaversetrajopt_b200.device_path import DevicePath
+    from riskaversetrajopt_b200.drone import drone_params as dp
+    DWs, masses, obs_Qs = (x[:40] for x in drone_seed0)
+    us = 0.1 * np.random.RandomState(0).randn(20, 3)
+    full = DevicePath(_lib.SAA_DRONE, 'saa', 20, 0.1, 40)
+    full.set_params_drone(dp, dp.OSQP_TOL); full.set_samples_drone(masses, DWs, obs_Qs)
+    sub = DevicePath(_lib.SAA_DRONE, 'saa', 20, 0.1, 32, M_global=40)
+    sub.set_params_drone(dp, dp.OSQP_TOL)
+    with pytest.raises(_lib.SaaError):
+        sub.set_active(33, 40, 0)
+    for pick, first in (([3, 5, 8, 13, 21], 7), (list(range(32)), 0), ([39], 11), ([], 4)):
+        K = len(pick)
+        idx = torch.as_tensor(pick + [0], dtype=torch.int64, device='cuda')
+        sub.set_active(K, 12 + K, first)
+        check(lib.saa_gather_samples(sub._h, full._h, idx.data_ptr(), sub._stream()), sub._h)
+        n_rows, _, nnz = sub.pattern_sizes(False)
+        out = dict(Ax=torch.full((nnz,), 7.0, dtype=torch.float64, device='cuda'),
+                   l=torch.full((n_rows,), 7.0, dtype=torch.float64, device='cuda'),
+                   u=torch.full((n_rows,), 7.0, dtype=torch.float64, device='cuda'), const_state=None)
+        sub.assemble(us, 2, out=out, write_shared=False, finalize=False)
+        # the same samples through a handle created for exactly K samples
+        if K == 0:
+            assert all(bool((out[k] == 7.0).all()) for k in ('Ax', 'l', 'u'))
+            continue
+        ref = DevicePath(_lib.SAA_DRONE, 'saa', 20, 0.1, K, M_global=40)
+        ref.set_params_drone(dp, dp.OSQP_TOL)
+        ref.set_samples_drone(masses[pick], DWs[pick], obs_Qs[pick])
+        ref.set_output_geometry(12 + K, first)
+        want = dict(Ax=torch.full((nnz,), 7.0, dtype=torch.float64, device='cuda'),
+                    l=torch.full((n_rows,), 7.0, dtype=torch.float64, device='cuda'),
+                    u=torch.full((n_rows,), 7.0, dtype=torch.float64, device='cuda'), const_state=None)
+        ref.assemble(us, 2, out=want, write_shared=False, finalize=False)
+        for k in ('Ax', 'l', 'u'):
+            assert torch.equal(out[k], want[k]), (k, K, first)
+        ref.close()
+    sub.close(); full.close()
