@@ -382,6 +382,61 @@ int saa_set_active(saa_handle *h, int64_t M_active, int64_t M_out, int64_t first
 int saa_gather_samples(saa_handle *dst, const saa_handle *src,
                        const int64_t *idx_dev, void *stream);
 
+
+/* ----------------------------------------------------------------------------------------------
+ * Device-resident ADMM for the CVaR program (second option).
+ *
+ * The QP the reference hands to OSQP every SCP iteration (drone/drone_risk.py:327-399 and 425-452,
+ * car/driving.py:331-397 and 423-441) is solved where its matrix already is.  The algorithm is OSQP's
+ * (ADMM, Ruiz equilibration, per-row rho, over-relaxation; Stellato et al. 2020); the linear system
+ * (P + sigma I + A' R A) x = rhs is solved through the arrow structure of A: Sherman-Morrison for the
+ * CVaR row, a diagonal y block, a Schur complement on the nu + 2 dense variables w = (u, slack, t).
+ * These entry points are the sample-sized passes (one warp per sample, values read in place from the
+ * Ax / l / u buffers of saa_linearize_assemble) and the one-block step for the dense variables; the
+ * O(nu^2) host logic (inverting the Schur complement, adapting rho, the termination test) is in
+ * riskaversetrajopt_b200/device_qp.py.  Sharded samples: all-reduce the reduced partials between a
+ * pass and saa_qp_dense_step (sum, or max where stated).  FP64, method 'saa', not the car's scp_iter 0.
+ * -------------------------------------------------------------------------------------------- */
+typedef struct saa_qp_sample_state {   /* device arrays over this handle's M_local samples */
+  double *Dy, *Ey, *Es;   /* Ruiz scalings: y_i column (M), "-y_i" row (M), sample rows (M * R)        */
+  double *xy, *rloc;      /* scaled y variables; sample-local part of the right-hand side (M each)    */
+  double *zy, *ly;        /* ADMM z and multiplier of the "-y_i" rows (M each)                        */
+  double *zs, *ls;        /* ... of the sample rows (M * R each)                                      */
+} saa_qp_sample_state;
+/* Sizes, row / column offsets, offsets into the packed state G of saa_qp_dense_step, per-u-column
+ * (offset, final rows, run length), the active columns and the pair table of saa_qp_gram_pass, as a
+ * flat int64 array (order: riskaversetrajopt_b200/device_qp.py:_Layout). */
+int saa_qp_layout(saa_handle *h, int64_t *out, int64_t cap);
+/* kind: 0 scale, 1 gram, 2 admm pass, 3 check -> grid size and partial-vector length of that pass */
+int saa_qp_partials(saa_handle *h, int kind, int64_t *nblocks, int64_t *plen);
+/* One Ruiz sweep (norms with the old scalings, sample-local scalings updated in place); partials are
+ * maxima: [0, nu) u-column norms, slack column, t column, max D_y. */
+int saa_qp_scale_pass(saa_handle *h, const void *Ax, const void *l, const void *u, const double *Dw,
+                      double Ec, const saa_qp_sample_state *st, double *partials, void *stream);
+/* Sample share of the Schur complement and of the Sherman-Morrison vectors (sums). */
+int saa_qp_gram_pass(saa_handle *h, const void *Ax, const void *l, const void *u, const double *Dw,
+                     double Ec, double rho, double sigma, const saa_qp_sample_state *st,
+                     double *partials, void *stream);
+/* One ADMM iteration's sample part: finishes the iteration whose x~_w = xt[0..nu+2), gamma' =
+ * xt[nu+2] the dense step produced (skipped when first != 0) and accumulates the next right-hand
+ * side: partials (sums) = [R_u (nu), R_slack, R_t, sigma_1, cv]. */
+int saa_qp_admm_pass(saa_handle *h, const void *Ax, const void *l, const void *u, const double *Dw,
+                     double Ec, double rho, double sigma, double alpha, const saa_qp_sample_state *st,
+                     const double *xt, int first, double *partials, void *stream);
+/* Termination-test pieces of the sample rows at x_w = xw_lamc[0..nu+2), CVaR multiplier
+ * xw_lamc[nu+2]: partials = [max |(Ax-z)/E|, max |Ax/E|, max |z/E|, max |(A'lam)_y/D_y| | sums:
+ * (A'lam)_u (nu), (A'lam)_slack, (A'lam)_t]. */
+int saa_qp_check_pass(saa_handle *h, const void *Ax, const void *l, const void *u, const double *Dw,
+                      double Ec, const saa_qp_sample_state *st, const double *xw_lamc,
+                      double *partials, void *stream);
+/* out[e] = max (e < n_max) or sum over the nblocks partial vectors, in a fixed order. */
+int saa_qp_reduce(saa_handle *h, const double *partials, int64_t nblocks, int64_t plen, int64_t n_max,
+                  double *out, void *stream);
+/* Dense variables and sample-independent rows: finishes the iteration on them (skipped when
+ * first != 0), completes the right-hand side from red = reduced partials of saa_qp_admm_pass and
+ * solves for the next x~_w, gamma' (written into G). */
+int saa_qp_dense_step(saa_handle *h, double *G, const double *red, int first, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,6 +32,10 @@ class HopperPoint(C.Structure):
                 ("t_risk", C.c_double), ("slack", C.c_double)]
 
 
+class QpSampleState(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("Dy", "Ey", "Es", "xy", "rloc", "zy", "ly", "zs", "ls")]
+
+
 class CarParams(C.Structure):
     _fields_ = [("dt", C.c_double), ("u_max", C.c_double), ("beta", C.c_double),
                 ("speed_ped_des", C.c_double), ("min_separation_distance", C.c_double),
@@ -108,6 +112,18 @@ _PROTOTYPES = {
     "saa_select_counts": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p]),
     "saa_select_finish": (C.c_int, [_H, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "saa_set_active": (C.c_int, [_H, C.c_int64, C.c_int64, C.c_int64]),
+    "saa_qp_layout": (C.c_int, [_H, C.c_void_p, C.c_int64]),
+    "saa_qp_partials": (C.c_int, [_H, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "saa_qp_scale_pass": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
+                                    C.c_void_p, C.c_void_p, C.c_void_p]),
+    "saa_qp_gram_pass": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
+                                   C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "saa_qp_admm_pass": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
+                                   C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "saa_qp_check_pass": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p]),
+    "saa_qp_reduce": (C.c_int, [_H, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
+    "saa_qp_dense_step": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
 }
 EXPORTS = tuple(_PROTOTYPES)
 

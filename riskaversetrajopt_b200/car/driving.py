@@ -117,6 +117,24 @@ class Model:
         from .. import tail_scp
         if tail is None:
             tail = self.method == 'saa' and self.M > tail_scp.DEFAULT_TAIL_THRESHOLD
+        if solver == 'device' and scp_iter == 0:
+            solver = None                   # the relaxed problem of scp_iter 0 (a handful of rows, driving.py:411-415)
+        if solver == 'device' and tail is False:
+            # the QP is solved where the matrix is (device_qp.DeviceQP); with tail=... the tail-reduced
+            # subproblem is solved there instead (TailSCP)
+            if self.method == 'saa':
+                from ..device_qp import DeviceQP
+                b = self.path.assemble(us_mat_p, scp_iter)
+                if getattr(self, '_dqp', None) is None:
+                    self.P, self.q = self.get_objective_coeffs()
+                    self._dqp = DeviceQP(self.path, eps_abs=OSQP_TOL, eps_rel=OSQP_TOL, polish=OSQP_POLISH, verbose=verbose)
+                    self._dqp.setup(self.P, self.q, b)
+                else:
+                    self._dqp.update(b)
+                self._tail, self.osqp_prob = None, self._dqp
+                return True
+            solver = None
+        self._dqp = None
         if tail is not False and tail is not None and self.method == 'saa' and scp_iter >= 1:
             if scp_iter == 1 or getattr(self, '_tail', None) is None:
                 opts = dict(tail) if isinstance(tail, dict) else {}
@@ -144,6 +162,11 @@ class Model:
         return True
 
     def solve(self, verbose=False):
+        if getattr(self, '_dqp', None) is not None:
+            self.res = self._dqp.solve()
+            if self.res.info.status != 'solved':
+                print("[solve]: Problem infeasible.")
+            return self.convert_us_vec_to_us_mat(self.res.u), self.res.t
         if getattr(self, '_tail', None) is not None:
             self.res, self.left_out_margin = self._tail.solve()
             self.osqp_prob = self._tail.prob

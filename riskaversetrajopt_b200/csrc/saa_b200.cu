@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <limits>
 
 #include "saa_common.cuh"
@@ -15,6 +16,7 @@
 #include "hopper_kernels.cuh"
 #include "tail_kernels.cuh"
 #include "generic_kernels.cuh"
+#include "qp_kernels.cuh"
 
 using namespace saa;
 
@@ -46,6 +48,7 @@ struct saa_handle {
   int problem = 0, method = 0, variant = 0, S = 0, precision = 64, device = 0;
   i64 M_local = 0, M_global = 0, sample_offset = 0;
   i64 M_cap = 0;                     // capacity (M_local at creation); saa_set_active may lower M_local
+  void *qp = nullptr;                // column / pair tables of the device QP (qp_host.cuh)
   double *d_select = nullptr; i64 select_len = 0;   // state / histogram / block counts of the radix select
   i64 M_out = 0, first_out = 0;
   double alpha = 0.1;
@@ -493,6 +496,7 @@ int64_t saa_mean_len(const saa_handle *h);
 #include "hopper_host.cuh"
 #include "tail_host.cuh"
 #include "generic_host.cuh"
+#include "qp_host.cuh"
 
 // =============================================================================
 // C ABI
@@ -544,6 +548,7 @@ int saa_destroy(saa_handle *h) {
   cudaFree(h->d_a); cudaFree(h->d_b); cudaFree(h->d_c); cudaFree(h->d_d);
   cudaFree(h->d_partials); cudaFree(h->d_sums); cudaFree(h->d_fin_off); cudaFree(h->d_relax_scratch);
   cudaFree(h->d_nonfinite); cudaFree(h->d_hopper_geo); cudaFree(h->d_means_scratch); cudaFree(h->d_select);
+  qp_free(h);
   delete h;
   return SAA_OK;
 }

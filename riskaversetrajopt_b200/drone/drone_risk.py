@@ -114,9 +114,18 @@ class Model:
         from ..qp import make_solver
         from .. import tail_scp
         scp_iter = 2
+        self._tail = self._dqp = None
         if tail is None:
             tail = self.method == 'saa' and self.M > tail_scp.DEFAULT_TAIL_THRESHOLD
-        self._tail = None
+        if solver == 'device' and (tail is False or self.method != 'saa'):
+            # solver='device': the QP is solved where the matrix is (device_qp.DeviceQP), nothing sample-sized
+            # crosses PCIe; with tail=... it is the tail-reduced subproblem that is solved there (TailSCP)
+            from ..device_qp import DeviceQP
+            self.P, self.q = self.get_objective_coeffs()
+            self._dqp = DeviceQP(self.path, eps_abs=OSQP_TOL, eps_rel=OSQP_TOL, polish=OSQP_POLISH, verbose=verbose)
+            self._dqp.setup(self.P, self.q, self.path.assemble(us_mat_p, scp_iter))
+            self.osqp_prob = self._dqp
+            return True
         if tail is not False and tail is not None and self.method == 'saa':
             opts = dict(tail) if isinstance(tail, dict) else {}
             margin = opts.get('margin', 0.25) if (tail is True or isinstance(tail, dict)) else float(tail)
@@ -134,6 +143,9 @@ class Model:
         return True
 
     def update_problem(self, us_mat_p, scp_iter=0, verbose=False):
+        if getattr(self, '_dqp', None) is not None:
+            self._dqp.update(self.path.assemble(us_mat_p, scp_iter))
+            return True
         if getattr(self, '_tail', None) is not None:
             self._tail.update(us_mat_p, scp_iter)
             return True
@@ -144,6 +156,11 @@ class Model:
         return True
 
     def solve(self, verbose=True):
+        if getattr(self, '_dqp', None) is not None:
+            self.res = self._dqp.solve()
+            if self.res.info.status != 'solved':
+                print("[solve]: Problem infeasible.")
+            return self.convert_us_vec_to_us_mat(self.res.u), self.res.t
         if getattr(self, '_tail', None) is not None:
             self.res, self.left_out_margin = self._tail.solve()
             self.osqp_prob = self._tail.prob

@@ -33,6 +33,14 @@ class TailSCP:
         m = self.model
         self.tail = m.tail_subproblem(K=K, margin=self.margin)
         self.P, self.q = self.tail.get_objective_coeffs(*m.get_objective_coeffs())
+        if self.solver_name == 'device':
+            # the reduced QP is solved where it was assembled: only (u, slack, t) come back
+            from .device_qp import DeviceQP
+            self.prob = _DeviceProb(DeviceQP(self.tail.sub, eps_abs=self.osqp_tol, eps_rel=self.osqp_tol,
+                                             polish=self.polish, verbose=self.verbose), self.tail)
+            self.prob.setup(self.P, self.q, us_mat, scp_iter)
+            self._last = (np.array(us_mat, dtype=np.float64), scp_iter)
+            return
         self.A, self.l, self.u, self.idx = self.tail.get_constraints_coeffs(us_mat, scp_iter)
         self.prob = make_solver(self.solver_name)
         self.prob.setup(self.P, self.q, self.A, self.l, self.u, eps_abs=self.osqp_tol, eps_rel=self.osqp_tol,
@@ -43,6 +51,10 @@ class TailSCP:
         self._define(us_mat, scp_iter)
 
     def update(self, us_mat, scp_iter):
+        if self.solver_name == 'device':
+            self.prob.update(us_mat, scp_iter)
+            self._last = (np.array(us_mat, dtype=np.float64), scp_iter)
+            return
         self.A, self.l, self.u, self.idx = self.tail.get_constraints_coeffs(us_mat, scp_iter, copy=False)
         self.prob.update(l=self.l, u=self.u)
         self.prob.update(Ax=self.A.data)
@@ -65,3 +77,21 @@ class TailSCP:
             tries += 1
             self.resolves += 1
             self._define(self._last[0], self._last[1], K=min(self.model.M, 2 * self.tail.K))
+
+
+class _DeviceProb:
+    """``DeviceQP`` on the tail-reduced subproblem, with the solve() result shaped like OSQP's (x = (u, ..., t))."""
+
+    def __init__(self, dqp, tail):
+        self.dqp, self.tail = dqp, tail
+
+    def setup(self, P, q, us_mat, scp_iter):
+        self.dqp.setup(P, q, self.tail.assemble(us_mat, scp_iter))
+
+    def update(self, us_mat, scp_iter):
+        # the selection changes with the iterate: sample k of the subproblem is another sample now.  The
+        # multipliers / y of the previous iterate are kept as a warm start all the same (most of the tail persists).
+        self.dqp.update(self.tail.assemble(us_mat, scp_iter))
+
+    def solve(self):
+        return self.dqp.solve()
