@@ -231,3 +231,72 @@ def test_two_ranks_tail_subproblem(problem, M, mode, exact, skew):
         assert np.allclose(Ax[fin], As.data[fin], rtol=1e-12, atol=1e-14)
         assert np.array_equal(l[nfin:], ls[nfin:]) and np.array_equal(u[nfin:], us_[nfin:])
         assert np.allclose(l[:nfin], ls[:nfin], rtol=1e-12, atol=1e-14) and np.allclose(u[:nfin], us_[:nfin], rtol=1e-12, atol=1e-14)
+
+
+def _qp_worker(rank, world, initfile, M, out):
+    import scipy.sparse as sp
+    import torch
+    import torch.distributed as dist
+    from riskaversetrajopt_b200 import _lib, dist as sd
+    from riskaversetrajopt_b200.device_path import DevicePath
+    from riskaversetrajopt_b200.device_qp import DeviceQP
+    from riskaversetrajopt_b200.drone import drone_params as dp
+    from riskaversetrajopt_b200.drone.drone_utils import sample_uncertain_parameters
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"file://{initfile}", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    np.random.seed(0)
+    DWs, masses, obs_Qs = sample_uncertain_parameters('saa', M=M)
+
+    def make(first, cnt):
+        p = DevicePath(_lib.SAA_DRONE, 'saa', 20, 0.1, cnt, M_global=M, sample_offset=first, device=rank)
+        p.set_params_drone(dp, dp.OSQP_TOL)
+        p.set_samples_drone(masses[first:first + cnt], DWs[first:first + cnt], obs_Qs[first:first + cnt])
+        return p
+    n = 62 + M
+    P = sp.lil_matrix((n, n))
+    P[:60, :60] = np.kron(np.eye(20), 2 * dp.dt * np.asarray(dp.R))
+    P[n - 2, n - 2] = 1e4
+    P = sp.csc_matrix(P)
+    q = np.zeros(n); q[-2] = 1e4
+    first, cnt = sd.shard_range(M, world, rank)
+    path = make(first, cnt)
+    asm = sd.ShardedAssembler(path, mode='sharded')          # compact row block per rank, global means
+    us = np.tile(np.array([0.01, 0.01, 0.0]), (20, 1))
+    dq = DeviceQP(path, group=dist.group.WORLD, eps_abs=1e-4, eps_rel=1e-4)
+    dq.setup(P, q, asm.step(us, 2))
+    single = sq = None
+    if rank == 0:
+        single = make(0, M)
+        sq = DeviceQP(single, eps_abs=1e-4, eps_rel=1e-4).setup(P, q, single.assemble(us, 2))
+    res = []
+    for it in range(4):
+        dq.update(asm.step(us, it))
+        r = dq.solve()
+        rec = dict(u=r.u, t=r.t, slack=r.slack, iters=r.info.iter, status=r.info.status)
+        if rank == 0:
+            sq.update(single.assemble(us, it))
+            r1 = sq.solve()
+            rec.update(u1=r1.u, t1=r1.t, iters1=r1.info.iter, status1=r1.info.status)
+        res.append(rec)
+        us = np.reshape(r.u, (3, 20), 'F').T
+    out[rank] = res
+    dist.destroy_process_group()
+
+
+def test_two_ranks_solve_the_qp_on_sharded_rows():
+    """The device ADMM over row blocks that stay sharded (one (nu + 4)-double all-reduce per iteration): every
+    rank gets the solution one GPU computes over all samples."""
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    mgr = mp.Manager()
+    out = mgr.dict()
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_qp_worker, args=(2, os.path.join(d, "init"), 301, out), nprocs=2, join=True)
+    for it, (a, b) in enumerate(zip(out[0], out[1])):
+        assert a['status'] == b['status'] == a['status1'] == 'solved'
+        assert a['iters'] == b['iters'] and np.array_equal(a['u'], b['u']) and a['t'] == b['t']   # replicated dense state
+        assert abs(a['iters'] - a['iters1']) <= 10
+        assert np.max(np.abs(a['u'] - a['u1'])) < (1e-7 if it == 0 else 1e-4) and abs(a['t'] - a['t1']) < 1e-4
