@@ -20,6 +20,9 @@ the all-reduce of the 123 sample-mean sums).  Prints ONE JSON line.
             (what a host solver can actually ingest at M = 10^6), N = 1.
   roofline: algorithmic bytes (10 144 B per sample, SURVEY 8d / DESIGN.md) /
             kernel time vs the measured HBM peak in MEASURED_PEAKS.json.
+  device_qp: the QP of the SCP iteration solved on the device (device_qp.DeviceQP, the OSQP
+            iteration with an arrow-structured linear solve) on the tail-reduced subproblem:
+            ms per ADMM iteration, setup / factorisation cost, one bounded solve, N = 1.
   problems: BASELINE configs 2 and 3 on the same GPU: car and hopper kernel times with
             their HBM and FP64 rooflines (FP64 peak measured live: saa_measure_fp64_peak).
   cpu_baseline: the oracle's C/OpenMP port on the host cores over a bounded sample.
@@ -423,6 +426,13 @@ def run_ours(args):
         except Exception as exc:
             tail = {"error": repr(exc)[:200]}
 
+    dqp = None
+    if world == 1 and not args.no_tail and not args.no_device_qp:
+        try:
+            dqp = measure_device_qp(model, us, scp_iter, stream)
+        except Exception as exc:
+            dqp = {"error": repr(exc)[:200]}
+
     # ---- BASELINE configs 2 and 3 on the same GPU -----------------------------------------------
     problems = None
     if world == 1 and not args.no_problems:
@@ -489,6 +499,8 @@ def run_ours(args):
     }
     if tail is not None:
         out["e2e_tail"] = tail
+    if dqp is not None:
+        out["device_qp"] = dqp
     if problems is not None:
         out["problems"] = problems
     if parity is not None:
@@ -522,6 +534,42 @@ def measure_tail(model, us, scp_iter, stream, device):
             "note": "all M samples are rolled out and ranked on the device every step; the QP handed to the host "
                     "solver is restricted to the K = 1.25 alpha M samples with the largest max-constraint value at the "
                     "iterate (exact when the samples left out stay inactive: TailSubproblem.left_out_margin)"}
+
+
+def measure_device_qp(model, us, scp_iter, stream):
+    """The convex solve is context, not the accelerated path (north_star) -- but at M = 10^6 no host solver takes
+    the QP.  ``DeviceQP`` runs OSQP's iteration on the tail-reduced subproblem where it was assembled; reported:
+    device time of one ADMM iteration (sample pass + reduction + dense step), the Ruiz scaling and factorisation
+    (Gram pass) costs, and one solve bounded at 300 iterations from a cold start."""
+    import torch
+    from riskaversetrajopt_b200.device_qp import DeviceQP
+    t = model.tail_subproblem(margin=0.25)
+    P, q = t.get_objective_coeffs(*model.get_objective_coeffs())
+    b = t.assemble(us, scp_iter)
+    dq = DeviceQP(t.sub, eps_abs=1e-3, eps_rel=1e-3, max_iter=300)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    dq.setup(P, q, b)
+    torch.cuda.synchronize(); setup_ms = (time.perf_counter() - t0) * 1e3
+    t0 = time.perf_counter(); dq.update(b); torch.cuda.synchronize(); update_ms = (time.perf_counter() - t0) * 1e3
+    dq._iterate(True)
+    n0 = dq.launches
+    it_ms = _device_time(lambda: dq._iterate(False), stream, n=30, warm=5)
+    per_iter_launches = (dq.launches - n0) // 35
+    dq2 = DeviceQP(t.sub, eps_abs=1e-3, eps_rel=1e-3, max_iter=300).setup(P, q, b)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    r = dq2.solve()
+    torch.cuda.synchronize(); solve_ms = (time.perf_counter() - t0) * 1e3
+    K = t.K
+    pass_bytes = K * ((1140 + 5 * 60 + 8) * 8 + (2 * 60 + 4) * 8)     # values + state read, z / multipliers written
+    return {"samples": K, "of": model.path.M_local, "rows": 61 * K + 68, "ms_per_admm_iter": it_ms,
+            "launches_per_iter": per_iter_launches,
+            "pass_bytes_per_iter": pass_bytes, "pass_GBps": pass_bytes / (it_ms * 1e-3) / 1e9,
+            "setup_ms": setup_ms, "update_ms": update_ms,
+            "solve": {"max_iter": 300, "iters": r.info.iter, "status": r.info.status, "ms": solve_ms,
+                      "t": float(r.t), "slack": float(r.slack)},
+            "what": "OSQP's ADMM on the tail-reduced CVaR QP (K samples, 61 K + 68 rows), matrix read in place from the "
+                    "assembled CSC values; setup = 10 Ruiz sweeps + Gram pass + 62x62 inverse; update = new values: Gram "
+                    "pass + inverse; only (u, slack, t) leave the device"}
 
 
 def measure_problems(args, device, stream):
@@ -775,6 +823,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gather", action="store_true")
     ap.add_argument("--no-tail", action="store_true")
+    ap.add_argument("--no-device-qp", action="store_true")
     ap.add_argument("--target-samples", type=int, default=1_000_000)
     args = ap.parse_args()
     if args.impl == "reference":

@@ -64,6 +64,10 @@ void qp_free(saa_handle *h) {
 enum { QP_SCALE = 0, QP_GRAM = 1, QP_PASS = 2, QP_CHECK = 3 };
 constexpr int kQpWarps = 4;
 
+// tuning switches of the ADMM pass (defaults = the measured best): staging buffers per warp, min blocks per SM
+int qp_nbuf() { static const int v = std::getenv("SAA_QP_NBUF") ? std::atoi(std::getenv("SAA_QP_NBUF")) : 1; return v == 2 ? 2 : 1; }
+int qp_minb() { static const int v = std::getenv("SAA_QP_MINB") ? std::atoi(std::getenv("SAA_QP_MINB")) : 2; return v; }
+
 int qp_plen(const saa_handle *h, const QpPlan *p, int kind) {
   const int nu = h->lay.nu, nb = p->nact + 2;
   switch (kind) {
@@ -75,7 +79,8 @@ int qp_plen(const saa_handle *h, const QpPlan *p, int kind) {
 }
 size_t qp_smem(const saa_handle *h, const QpPlan *p, int kind) {
   const int plen = qp_plen(h, p, kind);
-  const int per_warp = kind == QP_GRAM ? p->nnzJ + 2 * h->lay.R + p->nact + 2 : p->nnzJ + h->lay.R;
+  const int per_warp = kind == QP_GRAM ? p->nnzJ + 2 * h->lay.R + p->nact + 2
+                     : kind == QP_PASS ? qp_nbuf() * (p->nnzJ + 5 * h->lay.R + 8) + h->lay.R : p->nnzJ + h->lay.R;
   return sizeof(QpShared) + sizeof(double) * (size_t)kQpWarps * (plen + per_warp);
 }
 
@@ -90,13 +95,29 @@ int qp_grid(saa_handle *h, K kernel, size_t smem, int *blocks) {
   return SAA_OK;
 }
 
+// the compile-time-horizon kernels apply when the layout is the reference's (S = 20, two active axes per step)
+bool qp_fixed(const saa_handle *h, const QpPlan *p) {
+  return h->lay.S == kS && p->nact == 2 * (kS - 1) && (h->lay.blk == 3 || h->lay.blk == 1) && !h->qp_generic;
+}
+
+template <typename F>
+int qp_pass_dispatch(const saa_handle *h, const QpPlan *p, F &&f) {
+  const int mb = qp_minb();
+  if (!qp_fixed(h, p)) return f(qp_admm_pass_kernel<0, 0, 2>);
+  if (h->lay.blk == 3) return mb >= 4 ? f(qp_admm_pass_kernel<kS, 3, 4>) : mb == 3 ? f(qp_admm_pass_kernel<kS, 3, 3>) : f(qp_admm_pass_kernel<kS, 3, 2>);
+  return mb >= 4 ? f(qp_admm_pass_kernel<kS, 1, 4>) : mb == 3 ? f(qp_admm_pass_kernel<kS, 1, 3>) : f(qp_admm_pass_kernel<kS, 1, 2>);
+}
+
 int qp_blocks(saa_handle *h, const QpPlan *p, int kind, int *blocks) {
   const size_t smem = qp_smem(h, p, kind);
   switch (kind) {
     case QP_SCALE: return qp_grid(h, qp_scale_pass_kernel, smem, blocks);
     case QP_GRAM: return qp_grid(h, qp_gram_pass_kernel, smem, blocks);
-    case QP_PASS: return qp_grid(h, qp_admm_pass_kernel, smem, blocks);
-    default: return qp_grid(h, qp_check_pass_kernel, smem, blocks);
+    case QP_PASS:
+      return qp_pass_dispatch(h, p, [&](auto kernel) { return qp_grid(h, kernel, smem, blocks); });
+    default:
+      if (qp_fixed(h, p)) return h->lay.blk == 3 ? qp_grid(h, qp_check_pass_kernel<kS, 3>, smem, blocks) : qp_grid(h, qp_check_pass_kernel<kS, 1>, smem, blocks);
+      return qp_grid(h, qp_check_pass_kernel<0, 0>, smem, blocks);
   }
 }
 
@@ -206,7 +227,8 @@ int saa_qp_admm_pass(saa_handle *h, const void *Ax, const void *l, const void *u
   QP_COMMON(QP_PASS)
   if (!xt) return fail(h, SAA_ERR_ARG, "NULL argument");
   A.Ec = Ec; A.rho = rho; A.sigma = sigma; A.alpha = alpha; A.xt = xt; A.first = first;
-  qp_admm_pass_kernel<<<blocks, kQpWarps * 32, smem, s_>>>(A);
+  A.nbuf = qp_nbuf();
+  qp_pass_dispatch(h, p, [&](auto kernel) { kernel<<<blocks, kQpWarps * 32, smem, s_>>>(A); return 0; });
   SAA_CUDA(h, cudaGetLastError());
   return SAA_OK;
 }
@@ -216,7 +238,9 @@ int saa_qp_check_pass(saa_handle *h, const void *Ax, const void *l, const void *
   QP_COMMON(QP_CHECK)
   if (!xw_lamc) return fail(h, SAA_ERR_ARG, "NULL argument");
   A.Ec = Ec; A.xt = xw_lamc;
-  qp_check_pass_kernel<<<blocks, kQpWarps * 32, smem, s_>>>(A);
+  if (!qp_fixed(h, p)) qp_check_pass_kernel<0, 0><<<blocks, kQpWarps * 32, smem, s_>>>(A);
+  else if (h->lay.blk == 3) qp_check_pass_kernel<kS, 3><<<blocks, kQpWarps * 32, smem, s_>>>(A);
+  else qp_check_pass_kernel<kS, 1><<<blocks, kQpWarps * 32, smem, s_>>>(A);
   SAA_CUDA(h, cudaGetLastError());
   return SAA_OK;
 }

@@ -43,6 +43,7 @@ struct QpArgs {
   QpSampleState st;
   const double *xt;                // pass: x~_w (nu + 2) and gamma'; check: x_w (nu + 2) and lambda of the CVaR row
   int first;
+  int nbuf;                        // pass: staging buffers per warp (2 = the next sample is prefetched while this one is processed)
   double *partials;                // [gridDim.x][plen]
   int plen;
   // gram
@@ -91,7 +92,8 @@ __device__ __forceinline__ void qp_block_setup(const QpArgs &A, QpShared *sh, bo
 }
 
 // stage sample gi's Jacobian values: Jt[off_c + o * L_c + kk] = entry (row o*S + j+1+kk, column c)
-__device__ __forceinline__ void qp_load_sample(const QpArgs &A, const QpShared *sh, double *Jt, i64 gi, int lane) {
+__device__ __forceinline__ void qp_load_sample(const QpArgs &A, const QpShared *sh, double *Jt, i64 gi, int lane,
+                                               bool wait = true) {
   // asynchronous global -> shared copies (LDGSTS): all of the sample's column pieces are in flight at once
   const unsigned sbase = (unsigned)__cvta_generic_to_shared(Jt);
   for (int a = 0; a < A.nact; ++a) {
@@ -100,8 +102,10 @@ __device__ __forceinline__ void qp_load_sample(const QpArgs &A, const QpShared *
     for (int e = lane; e < c.len; e += 32)
       asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sbase + 8u * (unsigned)(c.off + e)), "l"(src + e) : "memory");
   }
-  asm volatile("cp.async.wait_all;" ::: "memory");
-  __syncwarp();
+  if (wait) {
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncwarp();
+  }
 }
 
 // sum_c J[r, c] * v[c] over the active columns for row r = o * S + kr
@@ -141,6 +145,87 @@ __device__ __forceinline__ double qp_col_absmax(const QpArgs &A, const QpCol &c,
   return s;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Horizon known at compile time (S = 20, the reference's): the same three primitives with every offset an
+// immediate.  Active column index = 2 j + a (a = control axis 0 / 1), L_j = S - 1 - j, packed offset
+// off(j, a) = BLK (2 sum_{j' < j} L_j' + a L_j).  S = 0 selects the run-time versions above.
+// ------------------------------------------------------------------------------------------------
+template <int S> __host__ __device__ constexpr int qp_sumL(int j) { return j * (S - 1) - j * (j - 1) / 2; }
+template <int S, int BLK> __host__ __device__ constexpr int qp_off(int j, int a) { return BLK * (2 * qp_sumL<S>(j) + a * (S - 1 - j)); }
+
+template <int S, int BLK>
+__device__ __forceinline__ void qp_load(const QpArgs &A, const QpShared *sh, double *Jt, i64 gi, int lane,
+                                        bool wait = true) {
+  if constexpr (S == 0) {
+    qp_load_sample(A, sh, Jt, gi, lane, wait);
+  } else {
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(Jt);
+    static_for<0, S - 1>([&](auto J) {
+      constexpr int j = decltype(J)::value, len = BLK * (S - 1 - j);
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        const double *src = A.Ax + A.cols[2 * j + a].gbase + gi * len;
+        constexpr int off0 = qp_off<S, BLK>(j, 0);
+        const unsigned dst = sbase + 8u * (unsigned)(off0 + a * len);
+        if (lane < len)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8u * lane), "l"(src + lane) : "memory");
+        if constexpr (len > 32) {
+          if (lane + 32 < len)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8u * (lane + 32)), "l"(src + lane + 32) : "memory");
+        }
+      }
+    });
+    if (wait) {
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      __syncwarp();
+    }
+  }
+}
+
+template <int S, int BLK>
+__device__ __forceinline__ double qp_row(const QpArgs &A, const QpShared *sh, const double *Jt, const double *v, int r) {
+  if constexpr (S == 0) {
+    return qp_row_dot(A, sh, Jt, v, r / A.S, r % A.S);
+  } else {
+    const int o = r / S, kr = r - o * S;
+    const int t0 = o * (S - 1) + kr - 1;         // entry (j, a) of this row: off(j, a) + t0 - j (o + 1)
+    double s = 0.0;
+    static_for<0, S - 1>([&](auto J) {
+      constexpr int j = decltype(J)::value;
+      if (j < kr) {
+        constexpr int off0 = qp_off<S, BLK>(j, 0), off1 = qp_off<S, BLK>(j, 1);
+        const int tj = t0 - j * (o + 1);
+        s = fma(Jt[off0 + tj], v[2 * j], s);
+        s = fma(Jt[off1 + tj], v[2 * j + 1], s);
+      }
+    });
+    return s;
+  }
+}
+
+// transposed product for active column `a` = lane (ROUND 0) or lane + 32 (ROUND 1)
+template <int S, int BLK, int ROUND>
+__device__ __forceinline__ double qp_col(const QpArgs &A, const QpShared *sh, const double *Jt, const double *w, int lane) {
+  const int a = lane + 32 * ROUND;
+  if (a >= A.nact) return 0.0;
+  if constexpr (S == 0) {
+    return qp_col_dot(A, sh->cols[a], Jt, w);
+  } else {
+    const int j = a >> 1, L = S - 1 - j;
+    const int off = BLK * (2 * (j * (S - 1) - j * (j - 1) / 2) + (a & 1) * L);
+    constexpr int KR0 = ROUND == 0 ? 1 : 17;      // columns 32.. have j >= 16
+    double s = 0.0;
+#pragma unroll
+    for (int o = 0; o < BLK; ++o) {
+      const double *Jc = Jt + off + o * L - 1 - j;
+#pragma unroll
+      for (int kr = KR0; kr < S; ++kr)
+        if (kr > j) s = fma(Jc[kr], w[o * S + kr], s);
+    }
+    return s;
+  }
+}
+
 // block-level reduction of per-warp accumulators into partials[blockIdx.x][..]; MAXN leading entries by max
 __device__ __forceinline__ void qp_block_reduce(double *scratch /* [warps][plen] */, const double *mine_lane0,
                                                  int plen, int n_max, double *out, int warp, int lane, int nwarps) {
@@ -158,13 +243,39 @@ __device__ __forceinline__ void qp_block_reduce(double *scratch /* [warps][plen]
 // multiplier update -- then the sample part of the next right-hand side.
 // partial layout: [0, nu) R_u, nu R_s, nu+1 R_t, nu+2 sigma1, nu+3 cv
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) qp_admm_pass_kernel(QpArgs A) {
+template <int S, int BLK, int MINB>
+__global__ void __launch_bounds__(128, MINB) qp_admm_pass_kernel(QpArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   QpShared *sh = reinterpret_cast<QpShared *>(smem_raw);
   const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double *scratch = reinterpret_cast<double *>(sh + 1);                  // [nwarps][plen]
-  double *Jt = scratch + nwarps * A.plen + warp * (A.nnzJ + A.R);
-  double *wv = Jt + A.nnzJ;
+  // per warp: two staging buffers -- the next sample's Jacobian values AND its state (scalings, bounds, z,
+  // multipliers) are in flight (cp.async) while this one is processed: no global load is waited for -- + wv
+  const int bstride = A.nnzJ + 5 * A.R + 8;
+  double *Jbuf = scratch + nwarps * A.plen + warp * (A.nbuf * bstride + A.R);
+  double *wv = Jbuf + A.nbuf * bstride;
+  auto stage = [&](double *dst, i64 s, i64 gi) {
+    qp_load<S, BLK>(A, sh, dst, gi, lane, false);
+    const unsigned sb = (unsigned)__cvta_generic_to_shared(dst + A.nnzJ);
+    auto cp8 = [&](unsigned d, const double *src) {
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
+    };
+    for (int r = lane; r < A.R; r += 32) {
+      const i64 gr = A.row_s0 + gi * A.R + r;
+      cp8(sb + 8u * r, A.st.Es + s * A.R + r);
+      cp8(sb + 8u * (A.R + r), A.l + gr);
+      cp8(sb + 8u * (2 * A.R + r), A.u + gr);
+      cp8(sb + 8u * (3 * A.R + r), A.st.zs + s * A.R + r);
+      cp8(sb + 8u * (4 * A.R + r), A.st.ls + s * A.R + r);
+    }
+    if (lane < 8) {
+      const double *src = lane == 0 ? A.st.Dy + s : lane == 1 ? A.st.Ey + s : lane == 2 ? A.st.xy + s
+                        : lane == 3 ? A.st.rloc + s : lane == 4 ? A.st.zy + s : lane == 5 ? A.st.ly + s
+                        : lane == 6 ? A.l + A.row_y0 + gi : A.u + A.row_y0 + gi;
+      cp8(sb + 8u * (5 * A.R + lane), src);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
   qp_block_setup(A, sh, true);
   const QpConsts k = sh->k;
   const int nu = A.nu;
@@ -172,10 +283,25 @@ __global__ void __launch_bounds__(128) qp_admm_pass_kernel(QpArgs A) {
   const double s_t = A.xt[nu], t_t = A.xt[nu + 1], gam = A.xt[nu + 2];
   const double alpha = A.alpha, sigma = A.sigma;
   double acc0 = 0.0, acc1 = 0.0, acc_s = 0.0, acc_t = 0.0, acc_s1 = 0.0, acc_cv = 0.0;
-  for (i64 s = (i64)blockIdx.x * nwarps + warp; s < A.M_local; s += (i64)gridDim.x * nwarps) {
+  const i64 s_first = (i64)blockIdx.x * nwarps + warp, s_step = (i64)gridDim.x * nwarps;
+  int buf = 0;
+  const bool dbl = A.nbuf == 2;
+  if (dbl && s_first < A.M_local) stage(Jbuf, s_first, A.first_out + s_first);
+  for (i64 s = s_first; s < A.M_local; s += s_step, buf ^= (dbl ? 1 : 0)) {
     const i64 gi = A.first_out + s;
-    qp_load_sample(A, sh, Jt, gi, lane);
-    const double Dy = A.st.Dy[s], Ey = A.st.Ey[s];
+    const double *Jt = Jbuf + buf * bstride;
+    const double *sbuf = Jt + A.nnzJ;            // [Es | l | u | zs | ls] (R each), then Dy Ey xy rloc zy ly l_y u_y
+    if (!dbl) {
+      stage(Jbuf, s, gi);
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    } else if (s + s_step < A.M_local) {
+      stage(Jbuf + (buf ^ 1) * bstride, s + s_step, gi + s_step);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncwarp();
+    const double Dy = sbuf[5 * A.R], Ey = sbuf[5 * A.R + 1];
     double Es[kQpMaxQ], rho_r[kQpMaxQ], lo[kQpMaxQ], hi[kQpMaxQ], zu[kQpMaxQ], z[kQpMaxQ], lam[kQpMaxQ];
     double sA = 0.0, sB = 0.0;
 #pragma unroll
@@ -183,30 +309,28 @@ __global__ void __launch_bounds__(128) qp_admm_pass_kernel(QpArgs A) {
       const int r = lane + 32 * q;
       Es[q] = rho_r[q] = zu[q] = z[q] = lam[q] = 0.0; lo[q] = hi[q] = 0.0;
       if (r < A.R) {
-        const i64 gr = A.row_s0 + gi * A.R + r;
-        Es[q] = A.st.Es[s * A.R + r];
-        rho_r[q] = qp_rho(A.l[gr], A.u[gr], Es[q], A.rho, lo[q], hi[q]);
-        z[q] = A.st.zs[s * A.R + r];
-        lam[q] = A.st.ls[s * A.R + r];
+        Es[q] = sbuf[r];
+        rho_r[q] = qp_rho(sbuf[A.R + r], sbuf[2 * A.R + r], Es[q], A.rho, lo[q], hi[q]);
+        z[q] = sbuf[3 * A.R + r];
+        lam[q] = sbuf[4 * A.R + r];
         const double yrS = Es[q] * k.yr * Dy;
         sA += rho_r[q] * yrS * yrS;
         if (!A.first) {
-          zu[q] = Es[q] * qp_row_dot(A, sh, Jt, sh->ud, r / A.S, r % A.S);
+          zu[q] = Es[q] * qp_row<S, BLK>(A, sh, Jt, sh->ud, r);
           sB += rho_r[q] * yrS * (zu[q] + Es[q] * k.tr * Dt * t_t);
         }
       }
     }
     sA = sum32(sA); sB = sum32(sB);
     double ylo, yhi;
-    const i64 gy = A.row_y0 + gi;
-    const double ry = qp_rho(A.l[gy], A.u[gy], Ey, A.rho, ylo, yhi);
+    const double ry = qp_rho(sbuf[5 * A.R + 6], sbuf[5 * A.R + 7], Ey, A.rho, ylo, yhi);
     const double ydS = Ey * k.yd * Dy, ysS = Ey * k.ys * Ds;
     const double a_i = sigma + ry * ydS * ydS + sA;
     const double e_i = A.Ec * k.cvar_y * Dy;
-    double xy = A.st.xy[s], zy = A.st.zy[s], ly = A.st.ly[s];
+    double xy = sbuf[5 * A.R + 2], zy = sbuf[5 * A.R + 4], ly = sbuf[5 * A.R + 5];
     if (!A.first) {
       const double bx = sB + ry * ydS * ysS * s_t;
-      const double yt = (A.st.rloc[s] + e_i * gam - bx) / a_i;
+      const double yt = (sbuf[5 * A.R + 3] + e_i * gam - bx) / a_i;
       acc_cv += e_i * yt;
       xy = alpha * yt + (1.0 - alpha) * xy;
       {
@@ -258,8 +382,8 @@ __global__ void __launch_bounds__(128) qp_admm_pass_kernel(QpArgs A) {
     acc_s1 += e_i * f;
     if (lane == 0) A.st.rloc[s] = rloc;
     __syncwarp();
-    if (lane < A.nact) acc0 += sh->dcol[lane] * qp_col_dot(A, sh->cols[lane], Jt, wv);
-    if (lane + 32 < A.nact) acc1 += sh->dcol[lane + 32] * qp_col_dot(A, sh->cols[lane + 32], Jt, wv);
+    if (lane < A.nact) acc0 += sh->dcol[lane] * qp_col<S, BLK, 0>(A, sh, Jt, wv, lane);
+    if (lane + 32 < A.nact) acc1 += sh->dcol[lane + 32] * qp_col<S, BLK, 1>(A, sh, Jt, wv, lane);
     __syncwarp();
   }
   double *mine = scratch + warp * A.plen;
@@ -277,6 +401,7 @@ __global__ void __launch_bounds__(128) qp_admm_pass_kernel(QpArgs A) {
 //                 [4, 4+nu) (A'lam)_u, 4+nu (A'lam)_s, 5+nu (A'lam)_t      (sample rows' share)
 // A.xt = (x_w (nu+2), lambda of the CVaR row)
 // ------------------------------------------------------------------------------------------------
+template <int S, int BLK>
 __global__ void __launch_bounds__(128) qp_check_pass_kernel(QpArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   QpShared *sh = reinterpret_cast<QpShared *>(smem_raw);
@@ -292,7 +417,7 @@ __global__ void __launch_bounds__(128) qp_check_pass_kernel(QpArgs A) {
   double acc0 = 0.0, acc1 = 0.0, acc_s = 0.0, acc_t = 0.0, m_rp = 0.0, m_ax = 0.0, m_z = 0.0, m_gy = 0.0;
   for (i64 s = (i64)blockIdx.x * nwarps + warp; s < A.M_local; s += (i64)gridDim.x * nwarps) {
     const i64 gi = A.first_out + s;
-    qp_load_sample(A, sh, Jt, gi, lane);
+    qp_load<S, BLK>(A, sh, Jt, gi, lane);
     const double Dy = A.st.Dy[s], Ey = A.st.Ey[s], xy = A.st.xy[s];
     double gy = 0.0, gt = 0.0;
 #pragma unroll
@@ -300,7 +425,7 @@ __global__ void __launch_bounds__(128) qp_check_pass_kernel(QpArgs A) {
       const int r = lane + 32 * q;
       if (r < A.R) {
         const double Es = A.st.Es[s * A.R + r], z = A.st.zs[s * A.R + r], lam = A.st.ls[s * A.R + r];
-        const double ax = Es * (qp_row_dot(A, sh, Jt, sh->ud, r / A.S, r % A.S) + k.yr * Dy * xy + k.tr * Dt * t_x);
+        const double ax = Es * (qp_row<S, BLK>(A, sh, Jt, sh->ud, r) + k.yr * Dy * xy + k.tr * Dt * t_x);
         m_rp = fmax(m_rp, fabs(ax - z) / Es);
         m_ax = fmax(m_ax, fabs(ax) / Es);
         m_z = fmax(m_z, fabs(z) / Es);
@@ -323,8 +448,8 @@ __global__ void __launch_bounds__(128) qp_check_pass_kernel(QpArgs A) {
       acc_t += gt;
     }
     __syncwarp();
-    if (lane < A.nact) acc0 += sh->dcol[lane] * qp_col_dot(A, sh->cols[lane], Jt, wv);
-    if (lane + 32 < A.nact) acc1 += sh->dcol[lane + 32] * qp_col_dot(A, sh->cols[lane + 32], Jt, wv);
+    if (lane < A.nact) acc0 += sh->dcol[lane] * qp_col<S, BLK, 0>(A, sh, Jt, wv, lane);
+    if (lane + 32 < A.nact) acc1 += sh->dcol[lane + 32] * qp_col<S, BLK, 1>(A, sh, Jt, wv, lane);
     __syncwarp();
   }
   m_rp = max32(m_rp); m_ax = max32(m_ax); m_z = max32(m_z);

@@ -49,6 +49,7 @@ struct saa_handle {
   i64 M_local = 0, M_global = 0, sample_offset = 0;
   i64 M_cap = 0;                     // capacity (M_local at creation); saa_set_active may lower M_local
   void *qp = nullptr;                // column / pair tables of the device QP (qp_host.cuh)
+  bool qp_generic = false;           // force the run-time-horizon QP kernels (SAA_QP_GENERIC=1; tests)
   double *d_select = nullptr; i64 select_len = 0;   // state / histogram / block counts of the radix select
   i64 M_out = 0, first_out = 0;
   double alpha = 0.1;
@@ -529,6 +530,7 @@ int saa_create(saa_handle **out, int problem, int method, int variant, int64_t M
   if (!h) return fail(nullptr, SAA_ERR_ARG, "out of host memory");
   h->problem = problem; h->method = method; h->variant = variant; h->S = S;
   h->precision = precision; h->device = device;
+  h->qp_generic = std::getenv("SAA_QP_GENERIC") != nullptr;
   h->M_local = M_local; h->M_cap = M_local; h->M_global = M_global; h->sample_offset = sample_offset; h->alpha = alpha;
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->n_sms = prop.multiProcessorCount;
