@@ -55,3 +55,36 @@ def test_python_shim_raises(drone_seed0):
     with pytest.raises(ValueError):
         Model(dp.S, DWs, masses, bad)                                                    # non-diagonal Q
     assert issubclass(SaaError, RuntimeError)
+
+
+def test_qp_entry_points_reject_what_they_cannot_solve(built_lib, drone_seed0):
+    """saa_qp_*: the CVaR ('saa') program in FP64 only; NULL arguments and bad kinds are status codes."""
+    import torch
+    from riskaversetrajopt_b200 import _lib
+    from riskaversetrajopt_b200.device_path import DevicePath
+    from riskaversetrajopt_b200.device_qp import DeviceQP
+    lib = built_lib.lib
+    buf = np.zeros(1 << 16, dtype=np.int64)
+    nb, pl = C.c_int64(), C.c_int64()
+    base = DevicePath(_lib.SAA_DRONE, 'baseline', 20, 0.1, 8)
+    assert lib.saa_qp_layout(base.handle, buf.ctypes.data, buf.size) == -1 and b"saa" in lib.saa_last_error(base.handle)
+    f32 = DevicePath(_lib.SAA_DRONE, 'saa', 20, 0.1, 8, precision='fp32')
+    assert lib.saa_qp_partials(f32.handle, 2, C.byref(nb), C.byref(pl)) == -1 and b"FP64" in lib.saa_last_error(f32.handle)
+    with pytest.raises(ValueError):
+        DeviceQP(f32)
+    p = DevicePath(_lib.SAA_DRONE, 'saa', 20, 0.1, 8)
+    assert lib.saa_qp_layout(p.handle, buf.ctypes.data, 10) == -1 and b"too small" in lib.saa_last_error(p.handle)
+    assert lib.saa_qp_layout(p.handle, None, 10) == -1
+    assert lib.saa_qp_partials(p.handle, 7, C.byref(nb), C.byref(pl)) == -1
+    assert lib.saa_qp_partials(p.handle, 2, C.byref(nb), C.byref(pl)) == 0 and pl.value == 64 and nb.value >= 1
+    assert lib.saa_qp_layout(p.handle, buf.ctypes.data, buf.size) == 0
+    assert list(buf[:5]) == [6, 60, 60, 20, 3] and buf[17] == 38 and buf[18] == 1140      # n_fin nu R S blk ... nact nnzJ
+    d = torch.zeros(64, dtype=torch.float64, device='cuda')
+    assert lib.saa_qp_admm_pass(p.handle, None, None, None, None, 1.0, 0.1, 1e-6, 1.6, None, None, 0, None, None) == -1
+    assert lib.saa_qp_reduce(p.handle, d.data_ptr(), 0, 64, 0, d.data_ptr(), None) == -1
+    assert lib.saa_qp_dense_step(p.handle, None, d.data_ptr(), 0, None) == -1
+    car = DevicePath(_lib.SAA_CAR, 'saa', 20, 0.1, 8)
+    assert lib.saa_qp_layout(car.handle, buf.ctypes.data, buf.size) == 0 and list(buf[:5]) == [4, 40, 20, 20, 1]
+    assert buf[17] == 38 and buf[18] == 380
+    for x in (base, f32, p, car):
+        x.close()

@@ -100,3 +100,29 @@ def test_tail_subproblem_solved_on_the_device():
         assert dev.res.info.status == 'solved' and host.res.info.status == 'solved'
         assert np.max(np.abs(us_h - us_d)) < 1e-4 and abs(t_h - t_d) < 1e-4, it
     assert dev.left_out_margin == host.left_out_margin or abs(dev.left_out_margin - host.left_out_margin) < 1e-3
+
+
+def test_device_qp_other_horizon():
+    """S = 12 goes through the run-time-horizon QP kernels (the compile-time ones are for the reference's S = 20)."""
+    from riskaversetrajopt_b200.device_qp import DeviceQP
+    from riskaversetrajopt_b200.drone import drone_params as dp
+    from riskaversetrajopt_b200.drone.drone_risk import Model
+    from riskaversetrajopt_b200.drone.drone_utils import sample_uncertain_parameters
+    from riskaversetrajopt_b200.qp import OSQPLike
+    np.random.seed(0)
+    DWs, masses, obs_Qs = sample_uncertain_parameters('saa', M=30)
+    model = Model(12, DWs[:, :12], masses, obs_Qs, 'saa', 0.1)
+    P, q = model.get_objective_coeffs()
+    us = model.initial_guess_us_mat()
+    A, l, u = model.get_constraints_coeffs(us, 2)
+    host = OSQPLike().setup(P, q, A, l, u, eps_abs=1e-4, eps_rel=1e-4, warm_start=True)
+    dq = DeviceQP(model.path, eps_abs=1e-4, eps_rel=1e-4).setup(P, q, model.path.assemble(us, 2))
+    for it in (0, 2, 3):
+        A, l, u = model.get_constraints_coeffs(us, it)
+        host.update(l=l, u=u); host.update(Ax=A.data)
+        dq.update(model.path.assemble(us, it))
+        r0, r1 = host.solve(), dq.solve()
+        assert r0.info.status == r1.info.status == 'solved'
+        assert abs(r0.info.iter - r1.info.iter) <= 10
+        assert np.max(np.abs(r0.x - r1.x)) < (1e-7 if it == 0 else 1e-4), it
+        us = model.convert_us_vec_to_us_mat(r0.x[:36])
