@@ -110,7 +110,7 @@ class Model:
         return A[:nrow].toarray(), l[:nrow], u[:nrow]
 
     # -- SCP glue (reference :423-456) ---------------------------------------------------
-    def define_problem(self, us_mat_p, scp_iter=0, verbose=False, solver=None, tail=None):
+    def define_problem(self, us_mat_p, scp_iter=0, verbose=False, solver=None, tail=None, solver_opts=None):
         """``tail`` as in the drone ``Model.define_problem``: None = automatic (tail-reduced subproblem from
         scp_iter >= 1 on when M > 20 000), False = the full problem as the reference, True / margin = tail."""
         from ..qp import make_solver
@@ -127,7 +127,7 @@ class Model:
                 b = self.path.assemble(us_mat_p, scp_iter)
                 if getattr(self, '_dqp', None) is None:
                     self.P, self.q = self.get_objective_coeffs()
-                    self._dqp = DeviceQP(self.path, eps_abs=OSQP_TOL, eps_rel=OSQP_TOL, polish=OSQP_POLISH, verbose=verbose)
+                    self._dqp = DeviceQP(self.path, **{**dict(eps_abs=OSQP_TOL, eps_rel=OSQP_TOL, polish=OSQP_POLISH, verbose=verbose), **(solver_opts or {})})
                     self._dqp.setup(self.P, self.q, b)
                 else:
                     self._dqp.update(b)
@@ -140,7 +140,7 @@ class Model:
                 opts = dict(tail) if isinstance(tail, dict) else {}
                 margin = opts.get('margin', 0.25) if (tail is True or isinstance(tail, dict)) else float(tail)
                 self._tail = tail_scp.TailSCP(self, n_u * S, OSQP_TOL, OSQP_POLISH, margin, solver, verbose,
-                                               max_resolves=opts.get('max_resolves', 0))
+                                               max_resolves=opts.get('max_resolves', 0), solver_opts=solver_opts)
                 self._tail.define(us_mat_p, scp_iter)
             else:
                 self._tail.update(us_mat_p, scp_iter)

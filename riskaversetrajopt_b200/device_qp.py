@@ -126,11 +126,15 @@ class DeviceQP:
                                  "with compact per-rank blocks (set_output_geometry(M_local, 0))")
             self.M_qp = M
         n = self.n = nu + self.M_qp + 2
-        P = np.asarray(P.todense()) if hasattr(P, 'todense') else np.asarray(P)
         if P.shape[0] != n:
             raise ValueError(f"P must be the objective over (u, y[{self.M_qp}], slack, t)")
-        self.P_uu = np.array(P[:nu, :nu], dtype=np.float64)
+        # only the blocks the reference's objective has (drone_risk.py:376-391): u block, slack and t diagonal;
+        # never densify P (n ~ 10^5..10^6)
+        blk = lambda a: np.asarray(a.todense() if hasattr(a, 'todense') else a, dtype=np.float64)
+        self.P_uu = blk(P[:nu, :nu])
         self.P_ss, self.P_tt = float(P[n - 2, n - 2]), float(P[n - 1, n - 1])
+        if hasattr(P, 'nnz') and P.nnz != np.count_nonzero(self.P_uu) + (self.P_ss != 0) + (self.P_tt != 0):
+            raise ValueError("DeviceQP expects P = blkdiag(P_uu, 0_y, p_slack, p_t)")
         q = np.asarray(q, dtype=np.float64)
         self.q_w = np.concatenate([q[:nu], [q[n - 2], q[n - 1]]])
         f64 = dict(dtype=torch.float64, device=self.dev)

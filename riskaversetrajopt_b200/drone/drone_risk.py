@@ -106,7 +106,7 @@ class Model:
         return A[:nrow].toarray(), l[:nrow], u[:nrow]
 
     # -- SCP glue (reference drone_risk.py:425-469), host solver = OSQP stand-in -----
-    def define_problem(self, us_mat_p, verbose=False, solver=None, tail=None):
+    def define_problem(self, us_mat_p, verbose=False, solver=None, tail=None, solver_opts=None):
         """``tail``: None = automatic (the tail-reduced subproblem when M > 20 000, where no host QP
         ingests the full matrix), False = always the full problem as the reference, True / a margin
         (float) / dict(margin=, max_resolves=) = the tail-reduced subproblem (``tail_scp``); ``self.left_out_margin``
@@ -122,7 +122,7 @@ class Model:
             # crosses PCIe; with tail=... it is the tail-reduced subproblem that is solved there (TailSCP)
             from ..device_qp import DeviceQP
             self.P, self.q = self.get_objective_coeffs()
-            self._dqp = DeviceQP(self.path, eps_abs=OSQP_TOL, eps_rel=OSQP_TOL, polish=OSQP_POLISH, verbose=verbose)
+            self._dqp = DeviceQP(self.path, **{**dict(eps_abs=OSQP_TOL, eps_rel=OSQP_TOL, polish=OSQP_POLISH, verbose=verbose), **(solver_opts or {})})
             self._dqp.setup(self.P, self.q, self.path.assemble(us_mat_p, scp_iter))
             self.osqp_prob = self._dqp
             return True
@@ -130,7 +130,7 @@ class Model:
             opts = dict(tail) if isinstance(tail, dict) else {}
             margin = opts.get('margin', 0.25) if (tail is True or isinstance(tail, dict)) else float(tail)
             self._tail = tail_scp.TailSCP(self, n_u * self.S, OSQP_TOL, OSQP_POLISH, margin, solver, verbose,
-                                               max_resolves=opts.get('max_resolves', 0))
+                                               max_resolves=opts.get('max_resolves', 0), solver_opts=solver_opts)
             self._tail.define(us_mat_p, scp_iter)
             self.osqp_prob = self._tail.prob
             return True

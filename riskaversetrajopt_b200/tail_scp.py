@@ -21,10 +21,12 @@ DEFAULT_TAIL_THRESHOLD = 20000      # Model(...).define_problem: M above this sw
 
 
 class TailSCP:
-    def __init__(self, model, n_ctrl, osqp_tol, polish, margin=0.25, solver=None, verbose=False, max_resolves=0):
+    def __init__(self, model, n_ctrl, osqp_tol, polish, margin=0.25, solver=None, verbose=False, max_resolves=0,
+                 solver_opts=None):
         self.model, self.nu = model, int(n_ctrl)
         self.osqp_tol, self.polish, self.solver_name, self.verbose = osqp_tol, polish, solver, verbose
         self.margin, self.max_resolves = margin, int(max_resolves)
+        self.solver_opts = dict(solver_opts or {})       # overrides of eps_abs / eps_rel / polish / max_iter ...
         self.tail = None
         self.resolves = 0
 
@@ -36,15 +38,17 @@ class TailSCP:
         if self.solver_name == 'device':
             # the reduced QP is solved where it was assembled: only (u, slack, t) come back
             from .device_qp import DeviceQP
-            self.prob = _DeviceProb(DeviceQP(self.tail.sub, eps_abs=self.osqp_tol, eps_rel=self.osqp_tol,
-                                             polish=self.polish, verbose=self.verbose), self.tail)
+            kw = dict(eps_abs=self.osqp_tol, eps_rel=self.osqp_tol, polish=self.polish, verbose=self.verbose)
+            kw.update(self.solver_opts)
+            self.prob = _DeviceProb(DeviceQP(self.tail.sub, **kw), self.tail)
             self.prob.setup(self.P, self.q, us_mat, scp_iter)
             self._last = (np.array(us_mat, dtype=np.float64), scp_iter)
             return
         self.A, self.l, self.u, self.idx = self.tail.get_constraints_coeffs(us_mat, scp_iter)
         self.prob = make_solver(self.solver_name)
-        self.prob.setup(self.P, self.q, self.A, self.l, self.u, eps_abs=self.osqp_tol, eps_rel=self.osqp_tol,
-                        warm_start=True, verbose=self.verbose, polish=self.polish)
+        kw = dict(eps_abs=self.osqp_tol, eps_rel=self.osqp_tol, warm_start=True, verbose=self.verbose, polish=self.polish)
+        kw.update(self.solver_opts)
+        self.prob.setup(self.P, self.q, self.A, self.l, self.u, **kw)
         self._last = (np.array(us_mat, dtype=np.float64), scp_iter)
 
     def define(self, us_mat, scp_iter):
