@@ -7,7 +7,8 @@ stays on the reference's host solver and is timed separately as context").  OSQP
 installed in this image, so two stand-ins are provided:
 
 * ``'admm'``  – a from-scratch implementation of the OSQP algorithm (Stellato et al.,
-  2020: ADMM, Ruiz equilibration, per-constraint and adaptive rho, warm start); because the
+  2020: ADMM, Ruiz equilibration, per-constraint and adaptive rho, warm start, solution
+  polishing on the guessed active set with iterative refinement); because the
   SAA programs have m ~ 61 n the KKT system is solved in its reduced n x n form
   (dense Cholesky / sparse LU), 2-3x faster than factorising the (n + m) system.
 * ``'highs'`` – HiGHS' QP active-set solver through SciPy's bundled (private) binding;
@@ -62,13 +63,13 @@ class OSQPLike:
         self.A = sp.csc_matrix(A, dtype=np.float64).copy()
         self.q = np.asarray(q, dtype=np.float64).copy()
         self.l, self.u = _bounds(l, u)
-        if polish:
-            # OSQP's polishing step returns a high-accuracy solution of the active-set KKT system;
-            # this stand-in has no polishing: ``polish=True`` is EMULATED by iterating to 1e-6 with a
-            # larger iteration cap (the SCP of the reference does not converge when its QPs are only
-            # solved to 3e-4, see examples/car_scp.py).  There are no infeasibility certificates: an
-            # infeasible QP runs to ``max_iter`` and reports 'maximum iterations reached'.
-            eps_abs, eps_rel, max_iter = min(eps_abs, 1e-6), min(eps_rel, 1e-6), max(max_iter, 200000)
+        # polish=True (the reference's setting, drone_risk.py:436-440): after ADMM reaches (eps_abs, eps_rel) the
+        # KKT system of the guessed active set is solved with iterative refinement (``_polish``, OSQP's
+        # polishing step).  If that does not improve both residuals -- OSQP then returns the unpolished
+        # solution, which is too coarse for the reference's SCP (examples/car_scp.py) -- this stand-in keeps
+        # iterating to 1e-6 instead.  There are no infeasibility certificates: an infeasible QP runs to
+        # ``max_iter`` and reports 'maximum iterations reached'.
+        self.polish = bool(polish)
         self.opts = SimpleNamespace(eps_abs=eps_abs, eps_rel=eps_rel, max_iter=max_iter, rho=rho,
                                     sigma=sigma, alpha=alpha, warm_start=warm_start, verbose=verbose,
                                     scaling=scaling, adaptive_rho_interval=adaptive_rho_interval,
@@ -163,9 +164,58 @@ class OSQPLike:
         t0 = time.perf_counter()
         if not o.warm_start:
             self.x[:], self.z[:], self.y[:] = 0.0, 0.0, 0.0
+        status, it = self._admm(o.eps_abs, o.eps_rel, o.max_iter)
+        self.polished = False
+        if self.polish and status == 'solved':
+            self.polished = self._polish()
+            if not self.polished and (o.eps_abs > 1e-6 or o.eps_rel > 1e-6):
+                status, it2 = self._admm(min(o.eps_abs, 1e-6), min(o.eps_rel, 1e-6), max(o.max_iter, 200000))
+                it += it2
+        xs = self.D * self.x
+        info = SimpleNamespace(status=status, iter=it, run_time=time.perf_counter() - t0, polished=self.polished,
+                               obj_val=float(0.5 * xs @ (self.P @ xs) + self.q @ xs))
+        return SimpleNamespace(x=xs, y=self.E * self.y / self.c, info=info)
+
+    def _polish(self, delta=1e-6, refine=5):
+        """OSQP's polishing: guess the active constraints from (z, y), solve
+        [[P + delta I, A_act'], [A_act, -delta I]] (x, y_act) = (-q, b_act) with iterative refinement against the
+        unregularised system, accept if both residuals improve.  Scaled quantities throughout."""
+        x, z, y, ls, us = self.x, self.z, self.y, self.ls, self.us
+        eq = np.abs(us - ls) < 1e-10
+        low = ((z - ls) < -y) | eq
+        upp = ((us - z) < y) & ~low
+        idx = np.flatnonzero(low | upp)
+        n, ma = self.n, idx.size
+        b = np.where(low, ls, us)[idx]
+        Aa = sp.csr_matrix(self.As)[idx]
+        Kreg = sp.bmat([[self.Ps + delta * sp.identity(n), Aa.T], [Aa, -delta * sp.identity(ma)]], format='csc')
+        Ktrue = sp.bmat([[self.Ps, Aa.T], [Aa, None]], format='csr') if ma else sp.csr_matrix(self.Ps)
+        rhs = np.concatenate([-self.qs, b])
+        try:
+            lu = spla.splu(Kreg)
+        except RuntimeError:
+            return False
+        sol = lu.solve(rhs)
+        for _ in range(refine):
+            sol = sol + lu.solve(rhs - Ktrue @ sol)
+        xp, ya = sol[:n], sol[n:]
+        if not np.all(np.isfinite(sol)):
+            return False
+        yp = np.zeros(self.m); yp[idx] = ya
+        Ax = self.As @ xp
+        zp = np.clip(Ax, ls, us)
+        rp0, rd0, _, _ = self._residuals(x, z, y)
+        rp1, rd1, _, _ = self._residuals(xp, zp, yp)
+        if (rp1 < rp0 and rd1 < rd0) or (rp1 < 1e-10 and rd1 < 1e-10):
+            self.x, self.z, self.y = xp, zp, yp
+            return True
+        return False
+
+    def _admm(self, eps_abs, eps_rel, max_iter):
+        o = self.opts
         x, z, y = self.x, self.z, self.y
         status, it = 'maximum iterations reached', 0
-        for it in range(1, o.max_iter + 1):
+        for it in range(1, max_iter + 1):
             xt = self._solve_S(o.sigma * x - self.qs + self.As.T @ (self.rho_v * z - y))
             zt = self.As @ xt                      # = z + (nu - y) / rho with nu = rho (A xt - z) + y
             x = o.alpha * xt + (1 - o.alpha) * x
@@ -173,8 +223,8 @@ class OSQPLike:
             z_new = np.clip(zr + y / self.rho_v, self.ls, self.us)
             y = y + self.rho_v * (zr - z_new)
             z = z_new
-            if it % o.check_interval == 0 or it == o.max_iter:
-                rp, rd, ep, ed = self._residuals(x, z, y)
+            if it % o.check_interval == 0 or it == max_iter:
+                rp, rd, ep, ed = self._residuals(x, z, y, eps_abs, eps_rel)
                 if rp <= ep and rd <= ed:
                     status = 'solved'
                     break
@@ -186,13 +236,11 @@ class OSQPLike:
                         self.rho = new_rho
                         self._factor()
         self.x, self.z, self.y = x, z, y
-        xs = self.D * x
-        info = SimpleNamespace(status=status, iter=it, run_time=time.perf_counter() - t0,
-                               obj_val=float(0.5 * xs @ (self.P @ xs) + self.q @ xs))
-        return SimpleNamespace(x=xs, y=self.E * y / self.c, info=info)
+        return status, it
 
-    def _residuals(self, x, z, y):
-        o = self.opts
+    def _residuals(self, x, z, y, eps_abs=None, eps_rel=None):
+        o = SimpleNamespace(eps_abs=self.opts.eps_abs if eps_abs is None else eps_abs,
+                            eps_rel=self.opts.eps_rel if eps_rel is None else eps_rel)
         Einv, Dinv = 1.0 / self.E, 1.0 / self.D
         Ax = self.As @ x
         Px = self.Ps @ x

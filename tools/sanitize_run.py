@@ -39,6 +39,13 @@ for M in sizes:
         b = m.path.buffers()
         m.path.linearize_factored(us, 2, fsp, fp, b['u'])
         m.path.expand_factored(2, fsp, fp, 0, M, b['Ax'])
+        if prec == "fp64":
+            # device ADMM: Ruiz sweeps, Gram pass, a few iterations, the termination test -- with the
+            # compile-time-horizon kernels, and (SAA_QP_GENERIC=1 in a second run) the run-time-horizon ones
+            from riskaversetrajopt_b200.device_qp import DeviceQP
+            P, q = m.get_objective_coeffs()
+            dq = DeviceQP(m.path, max_iter=20, scaling=2).setup(P, q, m.path.assemble(us, 2))
+            dq.solve()
         c = Car(M, 'saa', 0.05, precision=prec)
         usc = c.initial_guess_us_mat() + 0.1 * np.random.randn(20, 2)
         for it in (0, 1, 2):
@@ -46,6 +53,10 @@ for M in sizes:
         c.us_to_state_trajectories(usc)
         c.monte_carlo_constraints(usc)
         c.path.check_finite()
+        if prec == "fp64":
+            P, q = c.get_objective_coeffs()
+            dq = DeviceQP(c.path, max_iter=20, scaling=2).setup(P, q, c.path.assemble(usc, 2))
+            dq.solve()
         cb = Car(M, 'baseline', 0.05, precision=prec)
         cb.get_constraints_coeffs(usc, 0)
         h = hp.Model(M, 'saa', 0.2, precision=prec)
