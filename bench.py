@@ -763,6 +763,44 @@ def measure_target_config(args, rank, world, local_rank, device):
         res["sharded_fused_roofline"] = {"achieved_GBps_all_gpus": M_total * BYTES_PER_SAMPLE / (ms * 1e-3) / 1e9,
                                          "peak_GBps_all_gpus": peak * world,
                                          "frac": M_total * BYTES_PER_SAMPLE / (ms * 1e-3) / 1e9 / (peak * world)}
+        # the consumer of the sharded row blocks: the device ADMM over ALL M_total samples, one (nu + 4)-double
+        # all-reduce per iteration (device_qp.DeviceQP with group=WORLD); device-timed per ADMM iteration
+        if not args.no_device_qp:
+            try:
+                import scipy.sparse as sp
+                from riskaversetrajopt_b200.device_qp import DeviceQP
+                nq = 62 + M_total
+                Pq = sp.lil_matrix((nq, nq))
+                Pq[:60, :60] = np.kron(np.eye(S), 2 * dp.dt * np.asarray(dp.R))
+                Pq[nq - 2, nq - 2] = 1e4
+                qq = np.zeros(nq); qq[-2] = 1e4
+                bq = path.assemble(us, 2, finalize=False)
+                pm.finalize(bq, 2)
+                dq = DeviceQP(path, group=dist.group.WORLD, eps_abs=1e-3, eps_rel=1e-3, max_iter=100)
+                torch.cuda.synchronize(); t0 = time.perf_counter()
+                dq.setup(sp.csc_matrix(Pq), qq, bq)
+                torch.cuda.synchronize(); setup_ms = (time.perf_counter() - t0) * 1e3
+                dq._iterate(True)
+                for _ in range(5):
+                    dq._iterate(False)
+                torch.cuda.synchronize(); dist.barrier()
+                nit = 30
+                a, b_ = _events(2)
+                a.record(stream)
+                for _ in range(nit):
+                    dq._iterate(False)
+                b_.record(stream)
+                torch.cuda.synchronize(); dist.barrier()
+                t = torch.tensor([a.elapsed_time(b_) / nit], dtype=torch.float64, device=device)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                res["device_qp_sharded"] = {
+                    "samples_total": M_total, "rows_total": 61 * M_total + 68, "ms_per_admm_iter": float(t.item()),
+                    "setup_ms": setup_ms,
+                    "what": "OSQP's ADMM over the full CVaR QP with the row blocks left on their owners: per iteration one "
+                            "sample pass per rank, an all-reduce of 64 doubles, the replicated dense step"}
+                del dq
+            except Exception as exc:
+                res["device_qp_sharded"] = {"error": repr(exc)[:200]}
         pm.close()
         del pm, path
         torch.cuda.empty_cache()
