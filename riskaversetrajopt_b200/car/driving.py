@@ -153,9 +153,9 @@ class Model:
             # the pattern changes between iteration 0 and 1: set up again (:429-437)
             self.osqp_prob = make_solver(solver)
             l = np.where(np.isnan(self.l), -np.inf, self.l)   # OSQP rejects nan; rows are empty anyway
-            self.osqp_prob.setup(self.P, self.q, self.A, l, self.u, eps_abs=OSQP_TOL,
-                                 eps_rel=OSQP_TOL, warm_start=True, verbose=verbose,
-                                 polish=OSQP_POLISH)
+            self.osqp_prob.setup(self.P, self.q, self.A, l, self.u,
+                                 **{**dict(eps_abs=OSQP_TOL, eps_rel=OSQP_TOL, warm_start=True, verbose=verbose,
+                                           polish=OSQP_POLISH), **(solver_opts or {})})
         else:
             self.osqp_prob.update(l=self.l, u=self.u)
             self.osqp_prob.update(Ax=self.A.data)

@@ -65,6 +65,10 @@ __device__ __forceinline__ double qp_rho(double l_raw, double u_raw, double E, d
   if (ls <= -kQpInf && us >= kQpInf) return 1e-6;
   return rho;
 }
+// 1 / (that rho) without a division: rho takes three values per solve
+__device__ __forceinline__ double qp_inv_rho(double rho_r, double rho, double inv_rho) {
+  return rho_r == rho ? inv_rho : (rho_r == 1e-6 ? 1e6 : 1e-3 * inv_rho);
+}
 
 struct QpShared {                  // block-shared header of the dynamic shared memory
   QpCol cols[kQpMaxCols];          // copy for lane-indexed access (the uniform loops read the kernel parameters)
@@ -281,7 +285,7 @@ __global__ void __launch_bounds__(128, MINB) qp_admm_pass_kernel(QpArgs A) {
   const int nu = A.nu;
   const double Ds = A.Dw[nu], Dt = A.Dw[nu + 1];
   const double s_t = A.xt[nu], t_t = A.xt[nu + 1], gam = A.xt[nu + 2];
-  const double alpha = A.alpha, sigma = A.sigma;
+  const double alpha = A.alpha, sigma = A.sigma, inv_rho = 1.0 / A.rho;
   double acc0 = 0.0, acc1 = 0.0, acc_s = 0.0, acc_t = 0.0, acc_s1 = 0.0, acc_cv = 0.0;
   const i64 s_first = (i64)blockIdx.x * nwarps + warp, s_step = (i64)gridDim.x * nwarps;
   int buf = 0;
@@ -325,18 +329,18 @@ __global__ void __launch_bounds__(128, MINB) qp_admm_pass_kernel(QpArgs A) {
     double ylo, yhi;
     const double ry = qp_rho(sbuf[5 * A.R + 6], sbuf[5 * A.R + 7], Ey, A.rho, ylo, yhi);
     const double ydS = Ey * k.yd * Dy, ysS = Ey * k.ys * Ds;
-    const double a_i = sigma + ry * ydS * ydS + sA;
+    const double a_i = sigma + ry * ydS * ydS + sA, inv_a = 1.0 / a_i;
     const double e_i = A.Ec * k.cvar_y * Dy;
     double xy = sbuf[5 * A.R + 2], zy = sbuf[5 * A.R + 4], ly = sbuf[5 * A.R + 5];
     if (!A.first) {
       const double bx = sB + ry * ydS * ysS * s_t;
-      const double yt = (sbuf[5 * A.R + 3] + e_i * gam - bx) / a_i;
+      const double yt = (sbuf[5 * A.R + 3] + e_i * gam - bx) * inv_a;
       acc_cv += e_i * yt;
       xy = alpha * yt + (1.0 - alpha) * xy;
       {
         const double zt = ydS * yt + ysS * s_t;
         const double zr = alpha * zt + (1.0 - alpha) * zy;
-        const double zn = fmin(fmax(zr + ly / ry, ylo), yhi);
+        const double zn = fmin(fmax(fma(ly, qp_inv_rho(ry, A.rho, inv_rho), zr), ylo), yhi);
         ly += ry * (zr - zn);
         zy = zn;
       }
@@ -346,7 +350,7 @@ __global__ void __launch_bounds__(128, MINB) qp_admm_pass_kernel(QpArgs A) {
         if (r < A.R) {
           const double zt = zu[q] + Es[q] * (k.yr * Dy * yt + k.tr * Dt * t_t);
           const double zr = alpha * zt + (1.0 - alpha) * z[q];
-          const double zn = fmin(fmax(zr + lam[q] / rho_r[q], lo[q]), hi[q]);
+          const double zn = fmin(fmax(fma(lam[q], qp_inv_rho(rho_r[q], A.rho, inv_rho), zr), lo[q]), hi[q]);
           lam[q] += rho_r[q] * (zr - zn);
           z[q] = zn;
           A.st.zs[s * A.R + r] = zn;
@@ -366,7 +370,7 @@ __global__ void __launch_bounds__(128, MINB) qp_admm_pass_kernel(QpArgs A) {
     }
     sw = sum32(sw);
     const double rloc = sigma * xy + ydS * wy + sw;
-    const double f = rloc / a_i;
+    const double f = rloc * inv_a;
     double st_ = 0.0;
 #pragma unroll
     for (int q = 0; q < kQpMaxQ; ++q) {

@@ -138,8 +138,8 @@ class Model:
         self.A, self.l, self.u = self.get_constraints_coeffs(us_mat_p, scp_iter)
         self.osqp_prob = make_solver(solver)
         self.osqp_prob.setup(self.P, self.q, self.A, self.l, self.u,
-                             eps_abs=OSQP_TOL, eps_rel=OSQP_TOL, warm_start=True,
-                             verbose=verbose, polish=OSQP_POLISH)
+                             **{**dict(eps_abs=OSQP_TOL, eps_rel=OSQP_TOL, warm_start=True, verbose=verbose,
+                                       polish=OSQP_POLISH), **(solver_opts or {})})
         return True
 
     def update_problem(self, us_mat_p, scp_iter=0, verbose=False):

@@ -63,13 +63,18 @@ class OSQPLike:
         self.A = sp.csc_matrix(A, dtype=np.float64).copy()
         self.q = np.asarray(q, dtype=np.float64).copy()
         self.l, self.u = _bounds(l, u)
-        # polish=True (the reference's setting, drone_risk.py:436-440): after ADMM reaches (eps_abs, eps_rel) the
-        # KKT system of the guessed active set is solved with iterative refinement (``_polish``, OSQP's
-        # polishing step).  If that does not improve both residuals -- OSQP then returns the unpolished
-        # solution, which is too coarse for the reference's SCP (examples/car_scp.py) -- this stand-in keeps
-        # iterating to 1e-6 instead.  There are no infeasibility certificates: an infeasible QP runs to
-        # ``max_iter`` and reports 'maximum iterations reached'.
-        self.polish = bool(polish)
+        # polish=True (the reference's setting, drone_risk.py:436-440) is EMULATED by iterating to 1e-6 with a
+        # larger iteration cap: the SCP of the reference does not converge when its QPs are only solved to
+        # 3e-4 (examples/car_scp.py).  polish='kkt' runs OSQP's actual polishing step after ADMM reaches
+        # (eps_abs, eps_rel) -- the KKT system of the guessed active set with iterative refinement
+        # (``_polish``) -- and falls back to the emulation when the polished point does not improve both
+        # residuals.  On the CVaR programs that happens on every unrelaxed SCP iteration (the active set
+        # guessed at eps = 1e-3 is wrong: the program is degenerate), and mixing polished and unpolished
+        # iterations perturbs the trust-region-free SCP, so it is opt-in.  There are no infeasibility
+        # certificates: an infeasible QP runs to ``max_iter`` and reports 'maximum iterations reached'.
+        self.polish = polish == 'kkt'
+        if polish and not self.polish:
+            eps_abs, eps_rel, max_iter = min(eps_abs, 1e-6), min(eps_rel, 1e-6), max(max_iter, 200000)
         self.opts = SimpleNamespace(eps_abs=eps_abs, eps_rel=eps_rel, max_iter=max_iter, rho=rho,
                                     sigma=sigma, alpha=alpha, warm_start=warm_start, verbose=verbose,
                                     scaling=scaling, adaptive_rho_interval=adaptive_rho_interval,

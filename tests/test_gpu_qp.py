@@ -76,15 +76,15 @@ def test_scp_with_the_device_solver_reaches_the_host_solvers_trajectory():
     from riskaversetrajopt_b200.drone.drone_risk import L2_error_us
     host, dev = _drone_model(64), _drone_model(64)
     us_h = us_d = host.initial_guess_us_mat()
-    host.define_problem(us_h, tail=False)
-    dev.define_problem(us_d, solver='device')
+    opts = dict(eps_abs=1e-6, eps_rel=1e-6, polish=False, max_iter=200000)       # the same ADMM on both sides
+    host.define_problem(us_h, tail=False, solver_opts=opts)
+    dev.define_problem(us_d, solver='device', solver_opts=opts)
     for it in range(8):
         host.update_problem(us_h, it); us_h, t_h = host.solve(verbose=False)
         dev.update_problem(us_d, it); us_d, t_d = dev.solve(verbose=False)
         assert dev.res.info.status == 'solved'
-        # the host stand-in polishes where it can, the device solver iterates to 1e-6: same trajectory to ~1e-5
-        assert np.max(np.abs(us_h - us_d)) < 1e-4 and abs(t_h - t_d) < 1e-4, it
-    assert L2_error_us(us_d, us_h) < 1e-4
+        assert np.max(np.abs(us_h - us_d)) < 1e-5 and abs(t_h - t_d) < 1e-5, it
+    assert L2_error_us(us_d, us_h) < 1e-5
 
 
 def test_tail_subproblem_solved_on_the_device():
@@ -92,8 +92,9 @@ def test_tail_subproblem_solved_on_the_device():
     the device; the SCP follows the host-solved tail path."""
     host, dev = _drone_model(600), _drone_model(600)
     us_h = us_d = host.initial_guess_us_mat()
-    host.define_problem(us_h, tail=0.5)
-    dev.define_problem(us_d, tail=0.5, solver='device')
+    opts = dict(eps_abs=1e-6, eps_rel=1e-6, polish=False, max_iter=200000)       # the same ADMM on both sides
+    host.define_problem(us_h, tail=0.5, solver_opts=opts)
+    dev.define_problem(us_d, tail=0.5, solver='device', solver_opts=opts)
     assert dev._tail.tail.K == host._tail.tail.K
     for it in range(6):
         host.update_problem(us_h, it); us_h, t_h = host.solve(verbose=False)

@@ -58,3 +58,19 @@ def test_car_scp_converges_on_oracle_matrices():
         us = new
     assert r.info.status == 'solved' and err < 1e-2 and r.x[-1] <= 1e-6
     assert np.allclose(b.rollout(us)[0, -1, :4], [20, 0.1, 4.1, 0], atol=1e-3)
+
+
+def test_kkt_polish_gives_the_exact_solution_when_the_active_set_is_right():
+    """polish='kkt' (OSQP's polishing step): coarse ADMM + active-set KKT solve with iterative refinement."""
+    rs = np.random.RandomState(3)
+    n, m = 10, 30
+    Q = rs.randn(n, n); P = sp.csc_matrix(Q @ Q.T + np.eye(n)); q = rs.randn(n)
+    A = sp.csc_matrix(rs.randn(m, n)); l, u = -0.3 * np.ones(m), 0.3 * np.ones(m)
+    ref = make_solver('admm'); ref.setup(P, q, A, l, u, eps_abs=1e-10, eps_rel=1e-10)
+    x_ref = ref.solve().x
+    s = make_solver('admm'); s.setup(P, q, A, l, u, eps_abs=1e-3, eps_rel=1e-3, polish='kkt')
+    r = s.solve()
+    assert r.info.status == 'solved' and r.info.polished
+    assert np.max(np.abs(r.x - x_ref)) < 1e-8
+    coarse = make_solver('admm'); coarse.setup(P, q, A, l, u, eps_abs=1e-3, eps_rel=1e-3)
+    assert np.max(np.abs(coarse.solve().x - x_ref)) > 1e-6          # what polishing bought
