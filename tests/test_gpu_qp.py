@@ -128,3 +128,19 @@ def test_device_qp_other_horizon():
         assert abs(r0.info.iter - r1.info.iter) <= 10
         assert np.max(np.abs(r0.x - r1.x)) < (1e-7 if it == 0 else 1e-4), it
         us = model.convert_us_vec_to_us_mat(r0.x[:36])
+
+
+def test_car_scp_with_the_device_solver():
+    """Car Model.define_problem(us, it, solver='device'): iteration 0 (relaxed pattern, a handful of rows) goes to
+    the host solver, iterations >= 1 are solved on the device; same trajectory as the host path."""
+    from riskaversetrajopt_b200.car.driving import Model
+    opts = dict(eps_abs=1e-6, eps_rel=1e-6, polish=False, max_iter=200000)
+    np.random.seed(0); host = Model(30, 'saa', 0.1)
+    np.random.seed(0); dev = Model(30, 'saa', 0.1)
+    us_h = us_d = host.initial_guess_us_mat()
+    for it in range(5):
+        host.define_problem(us_h, it, tail=False, solver_opts=opts); us_h, t_h = host.solve()
+        dev.define_problem(us_d, it, solver='device', tail=False, solver_opts=opts); us_d, t_d = dev.solve()
+        assert (dev._dqp is None) == (it == 0)
+        assert dev.res.info.status == 'solved'
+        assert np.max(np.abs(us_h - us_d)) < 1e-5 and abs(t_h - t_d) < 1e-5, it
