@@ -23,6 +23,7 @@ the all-reduce of the 123 sample-mean sums).  Prints ONE JSON line.
   device_qp: the QP of the SCP iteration solved on the device (device_qp.DeviceQP, the OSQP
             iteration with an arrow-structured linear solve) on the tail-reduced subproblem:
             ms per ADMM iteration, setup / factorisation cost, one bounded solve, N = 1.
+  e2e_fp32: the plugin call of the optional FP32 storage mode (half the PCIe bytes), N = 1.
   problems: BASELINE configs 2 and 3 on the same GPU: car and hopper kernel times with
             their HBM and FP64 rooflines (FP64 peak measured live: saa_measure_fp64_peak).
   cpu_baseline: the oracle's C/OpenMP port on the host cores over a bounded sample.
@@ -433,10 +434,41 @@ def run_ours(args):
         except Exception as exc:
             dqp = {"error": repr(exc)[:200]}
 
+    # ---- the optional FP32 storage mode through the same plugin call (north_star: "an optional FP32 mode") ----
+    e2e32 = None
+    if world == 1 and not args.no_fp32_e2e:
+        try:
+            del model, path
+            torch.cuda.empty_cache()
+            DWs, masses, obs_Qs = synthetic_drone_samples(M, seed=rank, device=device)
+            model = Model(S, DWs, masses, obs_Qs, 'saa', 0.1, device=local_rank, precision='fp32')
+            path = model.path
+            torch.cuda.synchronize()
+            del DWs, masses, obs_Qs
+            model.DWs = model.masses = model.obs_Qs = None
+            path._keep = []
+            k32 = _device_time(lambda: path.assemble(us, scp_iter, finalize=False), stream, n=10, warm=3)
+            model.get_constraints_coeffs(us, scp_iter, copy=False)
+            model.get_constraints_coeffs(us, scp_iter, copy=False)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                A, l, u = model.get_constraints_coeffs(us, scp_iter, copy=False)
+            dt32 = (time.perf_counter() - t0) / 3
+            e2e32 = {"value": M * S / dt32, "unit": UNIT, "ms_per_step": dt32 * 1e3, "kernel_ms": k32,
+                     "h2d_bytes_per_step": int(us.nbytes), "d2h_bytes_per_step": int(path.d2h_bytes_per_call(scp_iter)),
+                     "A_dtype": str(A.dtype),
+                     "what": "Model(..., precision='fp32').get_constraints_coeffs(us, 2, copy=False): FP64 arithmetic, every "
+                             "value rounded once to FP32 (<= 6e-8 relative per entry, tests/test_gpu_drone.py), half the "
+                             "bytes over PCIe; A.data is float32"}
+            del A, l, u
+            path._pinned.clear(); path._csc_cache.clear(); path._host_state.clear()
+        except Exception as exc:
+            e2e32 = {"error": repr(exc)[:200]}
+
     # ---- BASELINE configs 2 and 3 on the same GPU -----------------------------------------------
     problems = None
     if world == 1 and not args.no_problems:
-        del model, path
+        model = path = None
         torch.cuda.empty_cache()
         try:
             problems = measure_problems(args, device, stream)
@@ -501,6 +533,8 @@ def run_ours(args):
         out["e2e_tail"] = tail
     if dqp is not None:
         out["device_qp"] = dqp
+    if e2e32 is not None:
+        out["e2e_fp32"] = e2e32
     if problems is not None:
         out["problems"] = problems
     if parity is not None:
@@ -862,6 +896,7 @@ def main():
     ap.add_argument("--no-gather", action="store_true")
     ap.add_argument("--no-tail", action="store_true")
     ap.add_argument("--no-device-qp", action="store_true")
+    ap.add_argument("--no-fp32-e2e", action="store_true")
     ap.add_argument("--target-samples", type=int, default=1_000_000)
     args = ap.parse_args()
     if args.impl == "reference":

@@ -23,6 +23,9 @@ def main():
     ap.add_argument("--eps", type=float, default=1e-4)
     ap.add_argument("--max-iter", type=int, default=20000)
     ap.add_argument("--alpha", type=float, default=0.1)
+    ap.add_argument("--rho-interval", type=int, default=50)
+    ap.add_argument("--relax", type=float, default=1.6)
+    ap.add_argument("--rho0", type=float, default=0.1)
     args = ap.parse_args()
     import torch
     from riskaversetrajopt_b200.drone import drone_params as dp
@@ -40,7 +43,8 @@ def main():
     model = Model(dp.S, DWs, masses, obs_Qs, 'saa', args.alpha)
     del DWs
     us = model.initial_guess_us_mat()
-    opts = dict(eps_abs=args.eps, eps_rel=args.eps, polish=False, max_iter=args.max_iter)
+    opts = dict(eps_abs=args.eps, eps_rel=args.eps, polish=False, max_iter=args.max_iter,
+                adaptive_rho_interval=args.rho_interval, alpha=args.relax, rho=args.rho0)
     t0 = time.perf_counter()
     model.define_problem(us, tail=0.25, solver='device', solver_opts=opts)
     torch.cuda.synchronize()

@@ -308,10 +308,11 @@ class DevicePath:
                     h[lo:hi].copy_(b[name][lo:hi], non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         arrs = [h.numpy() for h in outs]
-        if self.bits == 32:
-            arrs = [a.astype(np.float64) for a in arrs]      # the host solver wants doubles
-        elif copy:
-            arrs = [a.copy() for a in arrs]
+        if copy:
+            # private arrays; FP32 storage is widened here (the reference's boundary returns doubles and OSQP
+            # wants them) -- a host pass over all values.  copy=False returns the staging buffers as they are
+            # (float32 in the FP32 storage mode: half the PCIe bytes and no host pass).
+            arrs = [a.astype(np.float64) if self.bits == 32 else a.copy() for a in arrs]
         return arrs
 
     def d2h_bytes_per_call(self, scp_iter=2):
@@ -327,7 +328,7 @@ class DevicePath:
         data, l, u = self.assemble_host(us_mat, scp_iter, copy=copy, assembled=assembled)
         key = self._uses_relaxed_pattern(scp_iter)
         n_rows, n_cols, indptr, indices = self.pattern(key)
-        if not copy and self.bits == 64:
+        if not copy:
             A = self._csc_cache.get(key)
             if A is None or A.data.ctypes.data != data.ctypes.data:
                 A = sp.csc_matrix((data, indices, indptr), shape=(n_rows, n_cols), copy=False)

@@ -173,6 +173,12 @@ def test_fp32_mode_within_1e4(drone_seed0):
     assert np.max(np.abs(u[f] - ur[f]) / np.maximum(np.abs(ur[f]), 1e-30)) < RTOL32
     fl = np.isfinite(lr)
     assert np.max(np.abs(l[fl] - lr[fl]) / np.maximum(np.abs(lr[fl]), 1e-30)) < RTOL32
+    # default (copy=True): doubles like the reference's boundary; copy=False: the float32 staging buffers as they are
+    assert A.data.dtype == np.float64 and u.dtype == np.float64
+    A32, l32, u32 = model.get_constraints_coeffs(us, 2, copy=False)
+    assert A32.data.dtype == np.float32 and u32.dtype == np.float32 and l32.dtype == np.float32
+    assert np.array_equal(A32.data.astype(np.float64), A.data) and np.array_equal(A32.indices, A.indices)
+    assert np.array_equal(u32.astype(np.float64), u)
 
 
 def test_large_M_sampled_parity_and_properties():
