@@ -70,8 +70,8 @@ class OSQPLike:
         # (``_polish``) -- and falls back to the emulation when the polished point does not improve both
         # residuals.  On the CVaR programs that happens on every unrelaxed SCP iteration (the active set
         # guessed at eps = 1e-3 is wrong: the program is degenerate), and mixing polished and unpolished
-        # iterations perturbs the trust-region-free SCP, so it is opt-in.  There are no infeasibility
-        # certificates: an infeasible QP runs to ``max_iter`` and reports 'maximum iterations reached'.
+        # iterations perturbs the trust-region-free SCP, so it is opt-in.  Infeasible / unbounded programs end
+        # with OSQP's status strings 'primal infeasible' / 'dual infeasible' (``_certificates``).
         self.polish = polish == 'kkt'
         if polish and not self.polish:
             eps_abs, eps_rel, max_iter = min(eps_abs, 1e-6), min(eps_rel, 1e-6), max(max_iter, 200000)
@@ -216,11 +216,38 @@ class OSQPLike:
             return True
         return False
 
+    def _certificates(self, dx, dy, eps_inf=1e-4):
+        """OSQP's infeasibility certificates from the change of the iterates over one step (Stellato et al.
+        2020, section 3.4), on unscaled quantities: 'primal infeasible' if dy is (almost) in the null space of
+        A' and has negative support-function value on [l, u]; 'dual infeasible' if dx is a direction of
+        unbounded descent that keeps A dx inside the recession cone of [l, u]."""
+        dyu = self.E * dy / self.c
+        ndy = np.max(np.abs(dyu), initial=0.0)
+        if ndy > 1e-30:
+            up, lo = np.maximum(dyu, 0.0), np.minimum(dyu, 0.0)
+            if not (np.any((self.u >= _INF) & (up > eps_inf * ndy)) or np.any((self.l <= -_INF) & (lo < -eps_inf * ndy))):
+                fu, fl = np.where(self.u >= _INF, 0.0, self.u), np.where(self.l <= -_INF, 0.0, self.l)
+                if (np.max(np.abs(self.A.T @ dyu), initial=0.0) <= eps_inf * ndy
+                        and fu @ up + fl @ lo <= -eps_inf * ndy):
+                    return 'primal infeasible'
+        dxu = self.D * dx
+        ndx = np.max(np.abs(dxu), initial=0.0)
+        if ndx > 1e-30:
+            Adx = self.A @ dxu
+            ok_rows = np.all(np.where(self.u >= _INF, True, Adx <= eps_inf * ndx)
+                             & np.where(self.l <= -_INF, True, Adx >= -eps_inf * ndx))
+            if (ok_rows and np.max(np.abs(self.P @ dxu), initial=0.0) <= eps_inf * ndx
+                    and self.q @ dxu <= -eps_inf * ndx):
+                return 'dual infeasible'
+        return None
+
     def _admm(self, eps_abs, eps_rel, max_iter):
         o = self.opts
         x, z, y = self.x, self.z, self.y
         status, it = 'maximum iterations reached', 0
         for it in range(1, max_iter + 1):
+            if it % o.check_interval == 0:
+                x_prev, y_prev = x, y
             xt = self._solve_S(o.sigma * x - self.qs + self.As.T @ (self.rho_v * z - y))
             zt = self.As @ xt                      # = z + (nu - y) / rho with nu = rho (A xt - z) + y
             x = o.alpha * xt + (1 - o.alpha) * x
@@ -233,6 +260,11 @@ class OSQPLike:
                 if rp <= ep and rd <= ed:
                     status = 'solved'
                     break
+                if it % o.check_interval == 0 and it > 5 * o.check_interval:
+                    cert = self._certificates(x - x_prev, y - y_prev)
+                    if cert is not None:
+                        status = cert
+                        break
                 if o.adaptive_rho_interval and it % o.adaptive_rho_interval == 0:
                     num = rp / max(ep, 1e-30)
                     den = rd / max(ed, 1e-30)

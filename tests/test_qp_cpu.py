@@ -74,3 +74,17 @@ def test_kkt_polish_gives_the_exact_solution_when_the_active_set_is_right():
     assert np.max(np.abs(r.x - x_ref)) < 1e-8
     coarse = make_solver('admm'); coarse.setup(P, q, A, l, u, eps_abs=1e-3, eps_rel=1e-3)
     assert np.max(np.abs(coarse.solve().x - x_ref)) > 1e-6          # what polishing bought
+
+
+def test_infeasibility_certificates():
+    """Infeasible and unbounded programs end with OSQP's status strings instead of running to max_iter."""
+    P = sp.csc_matrix(np.eye(1)); q = np.zeros(1)
+    A = sp.csc_matrix(np.array([[1.0], [1.0]]))
+    s = make_solver('admm'); s.setup(P, q, A, np.array([1.0, -np.inf]), np.array([np.inf, 0.0]), max_iter=5000)
+    r = s.solve()
+    assert r.info.status == 'primal infeasible' and r.info.iter < 5000
+    P0 = sp.csc_matrix((2, 2)); q0 = np.array([-1.0, 0.0])
+    A0 = sp.csc_matrix(np.eye(2))
+    s = make_solver('admm'); s.setup(P0, q0, A0, np.zeros(2), np.array([np.inf, 1.0]), max_iter=5000)
+    r = s.solve()
+    assert r.info.status == 'dual infeasible' and r.info.iter < 5000
