@@ -251,7 +251,7 @@ int saa_qp_reduce(saa_handle *h, const double *partials, int64_t nblocks, int64_
   if (!h || !partials || !out) return fail(h, SAA_ERR_ARG, "NULL argument");
   if (nblocks < 1 || plen < 1) return fail(h, SAA_ERR_ARG, "empty reduction");
   SAA_CUDA(h, cudaSetDevice(h->device));
-  qp_reduce_kernel<<<(int)((plen + 127) / 128), 128, 0, (cudaStream_t)stream>>>(partials, (int)nblocks, (int)plen, (int)n_max, out);
+  qp_reduce_kernel<<<(int)((plen * 32 + 127) / 128), 128, 0, (cudaStream_t)stream>>>(partials, (int)nblocks, (int)plen, (int)n_max, out);
   SAA_CUDA(h, cudaGetLastError());
   return SAA_OK;
 }

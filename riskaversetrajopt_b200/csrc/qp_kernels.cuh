@@ -630,14 +630,25 @@ __global__ void __launch_bounds__(128) qp_gram_pass_kernel(QpArgs A) {
   qp_block_reduce(scratch, nullptr, A.plen, 0, A.partials + (i64)blockIdx.x * A.plen, warp, lane, nwarps);
 }
 
-// out[e] = reduce over blocks of partials[b][e]: the first n_max entries by max, the rest by sum (fixed order)
+// out[e] = reduce over blocks of partials[b][e]: the first n_max entries by max, the rest by sum.  One warp per
+// entry: lane l folds blocks l, l+32, ... in order, then a fixed shuffle tree -- the order depends only on nblocks
+// (bitwise reproducible for a given grid).
 __global__ void qp_reduce_kernel(const double *__restrict__ partials, int nblocks, int plen, int n_max,
                                  double *__restrict__ out) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (e >= plen) return;
-  double v = partials[e];
-  for (int b = 1; b < nblocks; ++b) v = e < n_max ? fmax(v, partials[(i64)b * plen + e]) : v + partials[(i64)b * plen + e];
-  out[e] = v;
+  const bool mx = e < n_max;
+  double v = mx ? -kQpInf : 0.0;
+  for (int b = lane; b < nblocks; b += 32) {
+    const double p = partials[(i64)b * plen + e];
+    v = mx ? fmax(v, p) : v + p;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double w = __shfl_xor_sync(0xffffffffu, v, o);
+    v = mx ? fmax(v, w) : v + w;
+  }
+  if (lane == 0) out[e] = v;
 }
 
 // ------------------------------------------------------------------------------------------------
