@@ -302,6 +302,22 @@ class ShardedAssembler:
         return 380 * p.M_out + 156
 
 
+def tie_quotas(gt_eq, K_total):
+    """Per-rank (count, ties taken) of an exact global top-``K_total`` selection, from every rank's
+    ``(#{Z > threshold}, #{Z == threshold})``: all values above the threshold are taken, the remaining places go to
+    the ties in rank order (= global index order, the tie rule of the single-GPU selection)."""
+    gt_eq = np.asarray(gt_eq, dtype=np.int64).reshape(-1, 2)
+    rem = int(K_total) - int(gt_eq[:, 0].sum())
+    if rem < 0 or rem > int(gt_eq[:, 1].sum()):
+        raise ValueError("inconsistent threshold counts for the requested K")
+    out = []
+    for gt, eq in gt_eq:
+        take = int(min(eq, rem))
+        rem -= take
+        out.append((int(gt) + take, take))
+    return out
+
+
 def exact_global_select(path, Z, K_total, idx_out, group=None):
     """Exact global top-``K_total`` of the sharded values ``Z`` (this rank's ``path.M_local`` of them):
     the library's radix select with its histogram all-reduced between the passes.  Writes this rank's
@@ -321,16 +337,9 @@ def exact_global_select(path, Z, K_total, idx_out, group=None):
     allc = [torch.zeros_like(cnt) for _ in range(world)]
     dist.all_gather(allc, cnt, group=group)
     allc = torch.stack(allc).cpu().numpy()                  # the one host synchronisation of the selection
-    rem = int(K_total) - int(allc[:, 0].sum())
-    counts = []
-    for r in range(world):
-        take = int(min(allc[r, 1], max(rem, 0)))
-        rem -= take
-        counts.append(int(allc[r, 0]) + take)
-        if r == rank:
-            mine = take
-    check(lib.saa_select_finish(h, Z.data_ptr(), mine, idx_out.data_ptr(), st), h)
-    return counts
+    quotas = tie_quotas(allc, K_total)
+    check(lib.saa_select_finish(h, Z.data_ptr(), quotas[rank][1], idx_out.data_ptr(), st), h)
+    return [c for c, _ in quotas]
 
 
 class ShardedTailAssembler:

@@ -72,3 +72,31 @@ def test_two_rank_shards_reassemble_to_the_global_problem(built_lib):
                 merged[dst:dst + o["cnt"] * L] = o["Ax"][src:src + o["cnt"] * L]
         assert np.array_equal(gub[o["first"] * 60:(o["first"] + o["cnt"]) * 60], o["ub"])
     assert np.array_equal(merged, gAx)
+
+
+def test_tie_quotas_of_the_exact_global_selection():
+    """Places left after the values above the threshold go to the ties in rank order."""
+    from riskaversetrajopt_b200.dist import tie_quotas
+    assert tie_quotas([(3, 0), (2, 0)], 5) == [(3, 0), (2, 0)]
+    assert tie_quotas([(3, 4), (2, 5), (0, 1)], 8) == [(6, 3), (2, 0), (0, 0)]          # 3 places, all to rank 0
+    assert tie_quotas([(0, 2), (0, 2), (0, 2)], 5) == [(2, 2), (2, 2), (1, 1)]          # everything ties
+    assert tie_quotas([(0, 0), (7, 1)], 8) == [(0, 0), (8, 1)]                          # a rank that contributes nothing
+    rs = np.random.RandomState(0)
+    for _ in range(50):
+        z = np.round(rs.randn(200) * 2)
+        cuts = np.sort(rs.choice(np.arange(1, 200), 3, replace=False))
+        parts = np.split(z, cuts)
+        K = int(rs.randint(1, 201))
+        thr = np.sort(z)[::-1][K - 1]
+        q = tie_quotas([((p > thr).sum(), (p == thr).sum()) for p in parts], K)
+        assert sum(c for c, _ in q) == K
+        # the union of the per-rank picks is the global top K with ties to the smaller global index
+        order = np.lexsort((np.arange(200), -z))[:K]
+        got, off = [], 0
+        for p, (c, take) in zip(parts, q):
+            loc = np.concatenate([np.flatnonzero(p > thr), np.flatnonzero(p == thr)[:take]])
+            got.append(np.sort(loc) + off); off += len(p)
+        assert np.array_equal(np.concatenate(got), np.sort(order))
+    import pytest
+    with pytest.raises(ValueError):
+        tie_quotas([(3, 0), (3, 0)], 5)
