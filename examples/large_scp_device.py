@@ -26,6 +26,12 @@ def main():
     ap.add_argument("--rho-interval", type=int, default=50)
     ap.add_argument("--relax", type=float, default=1.6)
     ap.add_argument("--rho0", type=float, default=0.1)
+    ap.add_argument("--rho-tol", type=float, default=5.0,
+                    help="re-factorise when rho should change by more than this factor (OSQP: 5).  Adapting more "
+                         "eagerly (1.3 every 30 iterations) needs 2.7x fewer iterations at M = 1e5 but does not "
+                         "converge within 20 000 at M = 1e6: not the default")
+    ap.add_argument("--reset-at", type=int, default=-1, help="forget the warm start at this SCP iteration")
+    ap.add_argument("--reset-rho", type=float, default=None)
     args = ap.parse_args()
     import torch
     from riskaversetrajopt_b200.drone import drone_params as dp
@@ -44,7 +50,8 @@ def main():
     del DWs
     us = model.initial_guess_us_mat()
     opts = dict(eps_abs=args.eps, eps_rel=args.eps, polish=False, max_iter=args.max_iter,
-                adaptive_rho_interval=args.rho_interval, alpha=args.relax, rho=args.rho0)
+                adaptive_rho_interval=args.rho_interval, adaptive_rho_tolerance=args.rho_tol, alpha=args.relax,
+                rho=args.rho0)
     t0 = time.perf_counter()
     model.define_problem(us, tail=0.25, solver='device', solver_opts=opts)
     torch.cuda.synchronize()
@@ -52,6 +59,8 @@ def main():
            "define_ms": (time.perf_counter() - t0) * 1e3, "iterations": []}
     for it in range(args.iters):
         t0 = time.perf_counter()
+        if it == args.reset_at:
+            model._tail.prob.dqp.reset(args.reset_rho)
         model.update_problem(us, it)
         torch.cuda.synchronize(); t1 = time.perf_counter()
         us_new, t_risk = model.solve(verbose=False)

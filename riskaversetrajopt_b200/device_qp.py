@@ -64,7 +64,8 @@ class _Layout:
 
 class DeviceQP:
     def __init__(self, path, group=None, sharded=None, eps_abs=1e-3, eps_rel=1e-3, max_iter=20000, rho=0.1, sigma=1e-6, alpha=1.6,
-                 scaling=10, adaptive_rho_interval=50, check_interval=10, polish=False, verbose=False):
+                 scaling=10, adaptive_rho_interval=50, adaptive_rho_tolerance=5.0, check_interval=10, polish=False,
+                 verbose=False):
         if path.method != 'saa' or path.bits != 64:
             raise ValueError("DeviceQP solves the FP64 CVaR ('saa') program")
         if polish:                 # as qp.OSQPLike: polishing is emulated by iterating further
@@ -76,6 +77,7 @@ class DeviceQP:
         self._sharded = bool(group is not None) if sharded is None else bool(sharded)
         self.o = SimpleNamespace(eps_abs=eps_abs, eps_rel=eps_rel, max_iter=max_iter, sigma=sigma, alpha=alpha,
                                  scaling=scaling, adaptive_rho_interval=adaptive_rho_interval,
+                                 adaptive_rho_tolerance=float(adaptive_rho_tolerance),
                                  check_interval=check_interval, verbose=verbose)
         self.rho = rho
         self.dev = path.device
@@ -290,6 +292,18 @@ class DeviceQP:
         put('Fs', Fs); put('ctS', ctS); put('slS', [slS]); put('vcw', vcw); put('rho', r); put('lo', ls); put('hi', us)
         put('Sinv', Sinv); put('h', h); put('pw', pw); put('scal', [eps_c, vp, o.sigma, o.alpha]); put('qw', qw)
 
+    def reset(self, rho=None):
+        """Forget the warm start (x, z, multipliers := 0) and optionally restart rho -- for a QP that has nothing in
+        common with the previous one (the step from the relaxed first SCP iterations to the real constraints)."""
+        for k in ("xy", "rloc", "zy", "ly", "zs", "ls"):
+            self.st[k].zero_()
+        O, L = self.L.off, self.L
+        for k, n in (("z", L.ng), ("lam", L.ng), ("xw", L.nw), ("xt", L.nw + 1)):
+            self.G[O[k]:O[k] + n].zero_()
+        if rho is not None:
+            self.rho = float(rho)
+        self._stale = True
+
     # -- OSQP-style update ---------------------------------------------------------------------------
     def update(self, b=None):
         """New matrix values / bounds in the assembled buffers (same pattern, same scaling)."""
@@ -368,10 +382,11 @@ class DeviceQP:
             if o.adaptive_rho_interval and it % o.adaptive_rho_interval == 0:
                 num, den = rp / max(ep, 1e-30), rd / max(ed, 1e-30)
                 new_rho = float(np.clip(self.rho * np.sqrt(num / max(den, 1e-30)), 1e-6, 1e6))
-                if new_rho > 5 * self.rho or new_rho < self.rho / 5:
+                if new_rho > o.adaptive_rho_tolerance * self.rho or new_rho < self.rho / o.adaptive_rho_tolerance:
                     self.rho = new_rho
                     self._factor()
                     self._stale = True
+                    self.refactorizations = getattr(self, 'refactorizations', 0) + 1
         L = self.L
         O = L.off
         xw = self.G[O['xw']:O['xw'] + L.nw].cpu().numpy()
