@@ -126,7 +126,7 @@ QpArgs qp_args(const saa_handle *h, const QpPlan *p, const double *Ax, const dou
   const Layout &L = h->lay;
   QpArgs A{};
   A.Ax = Ax; A.l = l; A.u = u;
-  A.M_local = h->M_local; A.first_out = h->first_out; A.M_out = L.M;
+  A.M_local = h->M_local; A.first_out = h->first_out;
   A.row_y0 = L.row_y0; A.row_s0 = L.row_s0; A.ycol0 = L.ycol0; A.slackcol = L.slackcol; A.tcol = L.tcol;
   A.R = L.R; A.S = L.S; A.blk = L.blk; A.nu = L.nu; A.nact = p->nact; A.nnzJ = p->nnzJ;
   for (int a = 0; a < p->nact; ++a) A.cols[a] = p->cols[a];

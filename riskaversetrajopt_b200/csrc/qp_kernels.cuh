@@ -34,7 +34,7 @@ struct QpSampleState {             // mirrors saa_qp_sample_state (include/saa_b
 
 struct QpArgs {
   const double *Ax, *l, *u;
-  i64 M_local, first_out, M_out;
+  i64 M_local, first_out;
   i64 row_y0, row_s0, ycol0, slackcol, tcol;
   int R, S, blk, nu, nact, nnzJ;
   QpCol cols[kQpMaxCols];          // by value: lives in the constant bank, read with warp-uniform loads
@@ -230,10 +230,9 @@ __device__ __forceinline__ double qp_col(const QpArgs &A, const QpShared *sh, co
   }
 }
 
-// block-level reduction of per-warp accumulators into partials[blockIdx.x][..]; MAXN leading entries by max
-__device__ __forceinline__ void qp_block_reduce(double *scratch /* [warps][plen] */, const double *mine_lane0,
-                                                 int plen, int n_max, double *out, int warp, int lane, int nwarps) {
-  (void)mine_lane0;
+// block-level reduction of the per-warp accumulators scratch[warp][plen] into out[plen]: the first n_max entries
+// by max, the others by sum, warps in order
+__device__ __forceinline__ void qp_block_reduce(const double *scratch, int plen, int n_max, double *out, int nwarps) {
   __syncthreads();
   for (int e = threadIdx.x; e < plen; e += blockDim.x) {
     double v = scratch[e];
@@ -396,7 +395,7 @@ __global__ void __launch_bounds__(128, MINB) qp_admm_pass_kernel(QpArgs A) {
   if (lane < A.nact) mine[sh->cols[lane].c] = acc0;
   if (lane + 32 < A.nact) mine[sh->cols[lane + 32].c] = acc1;
   if (lane == 0) { mine[nu] = acc_s; mine[nu + 1] = acc_t; mine[nu + 2] = acc_s1; mine[nu + 3] = acc_cv; }
-  qp_block_reduce(scratch, nullptr, A.plen, 0, A.partials + (i64)blockIdx.x * A.plen, warp, lane, nwarps);
+  qp_block_reduce(scratch, A.plen, 0, A.partials + (i64)blockIdx.x * A.plen, nwarps);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -466,7 +465,7 @@ __global__ void __launch_bounds__(128) qp_check_pass_kernel(QpArgs A) {
     mine[0] = m_rp; mine[1] = m_ax; mine[2] = m_z; mine[3] = m_gy;
     mine[4 + nu] = acc_s; mine[5 + nu] = acc_t;
   }
-  qp_block_reduce(scratch, nullptr, A.plen, 4, A.partials + (i64)blockIdx.x * A.plen, warp, lane, nwarps);
+  qp_block_reduce(scratch, A.plen, 4, A.partials + (i64)blockIdx.x * A.plen, nwarps);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -535,7 +534,7 @@ __global__ void __launch_bounds__(128) qp_scale_pass_kernel(QpArgs A) {
   if (lane < A.nact) mine[sh->cols[lane].c] = acc0;
   if (lane + 32 < A.nact) mine[sh->cols[lane + 32].c] = acc1;
   if (lane == 0) { mine[nu] = m_s; mine[nu + 1] = m_t; mine[nu + 2] = m_dy; }
-  qp_block_reduce(scratch, nullptr, A.plen, A.plen, A.partials + (i64)blockIdx.x * A.plen, warp, lane, nwarps);
+  qp_block_reduce(scratch, A.plen, A.plen, A.partials + (i64)blockIdx.x * A.plen, nwarps);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -627,7 +626,7 @@ __global__ void __launch_bounds__(128) qp_gram_pass_kernel(QpArgs A) {
     for (int a = lane; a < nb; a += 32) mine[A.npairs + a] += bv[a] * e_i * inv_a;    // h
     __syncwarp();
   }
-  qp_block_reduce(scratch, nullptr, A.plen, 0, A.partials + (i64)blockIdx.x * A.plen, warp, lane, nwarps);
+  qp_block_reduce(scratch, A.plen, 0, A.partials + (i64)blockIdx.x * A.plen, nwarps);
 }
 
 // out[e] = reduce over blocks of partials[b][e]: the first n_max entries by max, the rest by sum.  One warp per
