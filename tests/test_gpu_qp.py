@@ -144,3 +144,19 @@ def test_car_scp_with_the_device_solver():
         assert (dev._dqp is None) == (it == 0)
         assert dev.res.info.status == 'solved'
         assert np.max(np.abs(us_h - us_d)) < 1e-4 and abs(t_h - t_d) < 1e-4, it      # rounding differences grow along the SCP
+
+
+def test_reset_forgets_the_warm_start():
+    """DeviceQP.reset(): the next solve starts from zero like a freshly set-up solver (same iterates)."""
+    from riskaversetrajopt_b200.device_qp import DeviceQP
+    model = _drone_model(40)
+    P, q = model.get_objective_coeffs()
+    us = model.initial_guess_us_mat()
+    b = model.path.assemble(us, 0)             # the relaxed first iteration: converges in tens of iterations
+    a = DeviceQP(model.path, eps_abs=1e-4, eps_rel=1e-4).setup(P, q, b)
+    r0 = a.solve()
+    a.reset(rho=0.1)
+    a.update(b)
+    r1 = a.solve()
+    assert r0.info.status == r1.info.status == 'solved' and r0.info.iter == r1.info.iter
+    assert np.max(np.abs(r0.x - r1.x)) < 1e-9
