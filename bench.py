@@ -407,6 +407,8 @@ def run_ours(args):
         e2e = {"value": M_global * S / float(te.item()), "unit": UNIT,
                "h2d_bytes_per_step": int(us.nbytes), "d2h_bytes_per_step": int(path.d2h_bytes_per_call(scp_iter)),
                "ms_per_step": float(te.item()) * 1e3, "steps": n_e2e,
+               # the call is bound by the device -> host link: bytes per rank / time (PCIe Gen5 x16 ~ 56 GB/s measured)
+               "d2h_GBps_per_gpu": path.d2h_bytes_per_call(scp_iter) / float(te.item()) / 1e9, "bound": "pcie d2h",
                "call": "Model.get_constraints_coeffs(us, 2, copy=False) -> (A: scipy csc_matrix, l, u)"
                        if world == 1 else "per rank: assemble + all-reduced means, then DevicePath.csc(..., copy=False) "
                                           "(the delivery Model.get_constraints_coeffs makes) of the rank's row block",
@@ -456,7 +458,8 @@ def run_ours(args):
             dt32 = (time.perf_counter() - t0) / 3
             e2e32 = {"value": M * S / dt32, "unit": UNIT, "ms_per_step": dt32 * 1e3, "kernel_ms": k32,
                      "h2d_bytes_per_step": int(us.nbytes), "d2h_bytes_per_step": int(path.d2h_bytes_per_call(scp_iter)),
-                     "A_dtype": str(A.dtype),
+                     "A_dtype": str(A.dtype), "d2h_GBps_per_gpu": path.d2h_bytes_per_call(scp_iter) / dt32 / 1e9,
+                     "bound": "pcie d2h",
                      "what": "Model(..., precision='fp32').get_constraints_coeffs(us, 2, copy=False): FP64 arithmetic, every "
                              "value rounded once to FP32 (<= 6e-8 relative per entry, tests/test_gpu_drone.py), half the "
                              "bytes over PCIe; A.data is float32"}
